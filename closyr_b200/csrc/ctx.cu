@@ -1,0 +1,676 @@
+// ctx.cu -- the C-ABI shim (north star (2)): owns CUDA streams, device buffers and pinned staging for the
+// 1..8 GPUs of one box, keeps xs/ys resident across generations, shards a population across the devices.
+// Replaces the per-run marshalling of the reference (src/closyr/symbolic_regression.clj:355-383,
+// src/closyr/ops/common.clj:30-76) and the per-phenotype call of ops/score-fn (src/closyr/ops.clj:119-136).
+// There is deliberately no CPU path in this file: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/closyr_b200.h"
+#include "internal.hpp"
+#include "kernels.cuh"
+
+using namespace closyr;
+
+namespace closyr {
+
+size_t rank_scratch_bytes(int64_t n);
+int launch_rank(const double *scores, int64_t n, int64_t k, void *scratch, int64_t *out, void *stream);
+
+void *pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_free(void *p) { cudaFreeHost(p); }
+
+namespace {
+
+struct DevBuf {                       // grow-only device allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DevPop {                       // one resident population shard
+    DevBuf code, code_off, consts, const_off, meta, aux;
+    int64_t lo = 0, hi = 0;           // expression range of the caller's population held here
+    uint32_t code_base = 0, const_base = 0, max_code = 0, max_consts = 0;
+    DevPopulation view() const
+    {
+        DevPopulation v;
+        v.code = (const uint32_t *)code.p;
+        v.code_off = (const uint32_t *)code_off.p;
+        v.consts = (const double *)consts.p;
+        v.const_off = (const uint32_t *)const_off.p;
+        v.meta = (const uint32_t *)meta.p;
+        v.aux = (const uint32_t *)aux.p;
+        v.code_base = code_base;
+        v.const_base = const_base;
+        v.n_expr = hi - lo;
+        return v;
+    }
+    void release() { code.release(); code_off.release(); consts.release(); const_off.release(); meta.release(); aux.release(); }
+};
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    DevBuf xs, ys, scores, rflags, partials, partials_all, flush, eval_xs, eval_f, eval_status, rank_a, rank_b;
+    DevPop pop, eval_pop;
+    int64_t chunk_lo = 0, chunk_hi = 0;   // point-sharded mode: this device's chunk range
+};
+
+}  // namespace
+}  // namespace closyr
+
+struct closyr_ctx {
+    std::vector<DeviceState> devs;
+    uint32_t flags = 0;
+    int64_t n_points = -1;
+    int64_t n_expr = -1;              // resident population size, -1 = none
+    bool scored = false;
+    int64_t launches = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+int fail(closyr_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    set_error(msg);
+    return code;
+}
+
+#define CU(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            cudaGetLastError();                                                                           \
+            return fail(ctx, CLOSYR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+        }                                                                                                 \
+    } while (0)
+
+int64_t n_chunks_of(int64_t n) { return (n + CHUNK_POINTS - 1) / CHUNK_POINTS; }
+int64_t pow2_ceil(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
+
+// copies expressions [lo, hi) of `pop` to the device
+int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_population *pop, int64_t lo, int64_t hi)
+{
+    CU(ctx, cudaSetDevice(d.device));
+    dp.lo = lo;
+    dp.hi = hi;
+    const int64_t ne = hi - lo;
+    if (ne <= 0) return CLOSYR_OK;
+    dp.code_base = pop->code_off[lo];
+    dp.const_base = pop->const_off[lo];
+    const size_t ncode = pop->code_off[hi] - dp.code_base, nk = pop->const_off[hi] - dp.const_base;
+    uint32_t mc = 0, mk = 0;
+    for (int64_t e = lo; e < hi; e++) {
+        mc = std::max(mc, pop->code_off[e + 1] - pop->code_off[e]);
+        mk = std::max(mk, pop->const_off[e + 1] - pop->const_off[e]);
+    }
+    if (mc > CLOSYR_MAX_CODE_WORDS || mk > CLOSYR_MAX_CONSTS)
+        return fail(ctx, CLOSYR_E_ARG, "population holds a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS");
+    dp.max_code = mc;
+    dp.max_consts = mk;
+    CU(ctx, dp.code.reserve(ncode * 4 + 16));
+    CU(ctx, dp.consts.reserve(nk * 8 + 16));
+    CU(ctx, dp.code_off.reserve((ne + 1) * 4));
+    CU(ctx, dp.const_off.reserve((ne + 1) * 4));
+    CU(ctx, dp.meta.reserve(ne * 4));
+    CU(ctx, dp.aux.reserve(ne * 4));
+    if (ncode) CU(ctx, cudaMemcpyAsync(dp.code.p, pop->code + dp.code_base, ncode * 4, cudaMemcpyHostToDevice, d.stream));
+    if (nk) CU(ctx, cudaMemcpyAsync(dp.consts.p, pop->consts + dp.const_base, nk * 8, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaMemcpyAsync(dp.code_off.p, pop->code_off + lo, (ne + 1) * 4, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaMemcpyAsync(dp.const_off.p, pop->const_off + lo, (ne + 1) * 4, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaMemcpyAsync(dp.meta.p, pop->meta + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaMemcpyAsync(dp.aux.p, pop->aux + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
+    return CLOSYR_OK;
+}
+
+int check_population(closyr_ctx *ctx, const closyr_population *pop)
+{
+    if (!pop || pop->n_expr < 0) return fail(ctx, CLOSYR_E_ARG, "bad population");
+    if (pop->n_expr > 0 && (!pop->code || !pop->code_off || !pop->const_off || !pop->meta || !pop->aux))
+        return fail(ctx, CLOSYR_E_ARG, "population has NULL arrays");
+    if (pop->n_expr > 0 && pop->const_off[pop->n_expr] > pop->const_off[0] && !pop->consts)
+        return fail(ctx, CLOSYR_E_ARG, "population has NULL constant pool");
+    return CLOSYR_OK;
+}
+
+// tile size (in chunks, power of two) so that the launch has enough warps to fill the GPU
+int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
+{
+    const int64_t target_items = 148 * 16 * 6;
+    int64_t cpt = pow2_ceil(std::max<int64_t>(1, nchunks));
+    while (cpt > 1 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;
+    return (int32_t)cpt;
+}
+
+// scores chunks [c_lo, c_hi) of the resident shard; leaves one partial triple per expression in
+// d.partials ([n_expr][3]) unless the range covers every point and fits one tile (then scores directly).
+int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_lo, int64_t c_hi, bool want_final,
+                 double *partials_out)
+{
+    const DevPopulation pv = d.pop.view();
+    const int64_t ne = pv.n_expr;
+    if (ne <= 0) return CLOSYR_OK;
+    const int64_t nch = c_hi - c_lo;
+    const int32_t cpt = pick_chunks_per_tile(ne, nch);
+    const int32_t n_tiles = (int32_t)std::max<int64_t>(1, (nch + cpt - 1) / cpt);
+    ScoreParams sp;
+    sp.pop = pv;
+    sp.xs = (const double *)d.xs.p;
+    sp.ys = (const double *)d.ys.p;
+    sp.n = ctx->n_points;
+    sp.chunk_begin = c_lo;
+    sp.chunk_end = c_hi;
+    sp.chunks_per_tile = cpt;
+    sp.n_tiles = n_tiles;
+    sp.max_leafs = max_leafs;
+    sp.scores = (double *)d.scores.p;
+    sp.rflags = (uint8_t *)d.rflags.p;
+    sp.partials = nullptr;
+    sp.partial_tile_offset = 0;
+    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts);
+    const bool direct = want_final && n_tiles == 1;
+    sp.final_scores = direct ? 1 : 0;
+    if (!direct) {
+        if (n_tiles == 1 && partials_out) sp.partials = partials_out;
+        else {
+            CU(ctx, d.partials.reserve((size_t)n_tiles * ne * 3 * 8));
+            sp.partials = (double *)d.partials.p;
+        }
+    }
+    launch_score(sp, smem, d.stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    if (!direct && !(n_tiles == 1 && partials_out)) {
+        FinalizeParams fp;
+        fp.meta = pv.meta;
+        fp.partials = (const double *)d.partials.p;
+        fp.n_expr = ne;
+        fp.n_tiles_total = n_tiles;
+        fp.max_leafs = max_leafs;
+        fp.n = ctx->n_points;
+        fp.scores = (double *)d.scores.p;
+        fp.rflags = (uint8_t *)d.rflags.p;
+        fp.out_partials = want_final ? nullptr : partials_out;
+        launch_finalize(fp, d.stream);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return CLOSYR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *closyr_last_error(const closyr_ctx *ctx)
+{
+    if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+int closyr_ctx_create(const int *devices, int n_devices, uint32_t flags, closyr_ctx **out)
+{
+    if (!out || n_devices < 1 || n_devices > 64) return fail(nullptr, CLOSYR_E_ARG, "bad arguments to closyr_ctx_create");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CLOSYR_E_NO_GPU,
+                    std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                        "); closyr_b200 has no CPU fallback");
+    }
+    closyr_ctx *ctx = new closyr_ctx();
+    ctx->flags = flags;
+    for (int i = 0; i < n_devices; i++) {
+        DeviceState d;
+        d.device = devices ? devices[i] : i;
+        if (d.device < 0 || d.device >= count) {
+            delete ctx;
+            return fail(nullptr, CLOSYR_E_ARG, "device index out of range");
+        }
+        ctx->devs.push_back(d);
+    }
+    for (auto &d : ctx->devs) {
+        cudaError_t r = cudaSetDevice(d.device);
+        if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (r == cudaSuccess) r = cudaEventCreate(&d.ev0);
+        if (r == cudaSuccess) r = cudaEventCreate(&d.ev1);
+        if (r == cudaSuccess) r = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming);
+        if (r != cudaSuccess) {
+            std::string m = std::string("CUDA initialisation failed: ") + cudaGetErrorString(r);
+            closyr_ctx_destroy(ctx);
+            return fail(nullptr, CLOSYR_E_CUDA, m);
+        }
+    }
+    if (ctx->devs.size() > 1 && (flags & CLOSYR_SHARD_POINTS)) {
+        for (size_t i = 1; i < ctx->devs.size(); i++) {       // device 0 gathers the partials over NVLink
+            cudaSetDevice(ctx->devs[0].device);
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->devs[0].device, ctx->devs[i].device);
+            if (can) { cudaDeviceEnablePeerAccess(ctx->devs[i].device, 0); cudaGetLastError(); }
+        }
+    }
+    *out = ctx;
+    return CLOSYR_OK;
+}
+
+void closyr_ctx_destroy(closyr_ctx *ctx)
+{
+    if (!ctx) return;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (DevBuf *b : { &d.xs, &d.ys, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
+                           &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b })
+            b->release();
+        d.pop.release();
+        d.eval_pop.release();
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.done) cudaEventDestroy(d.done);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int closyr_ctx_device_count(const closyr_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int closyr_set_points(closyr_ctx *ctx, const double *xs, const double *ys, int64_t n)
+{
+    if (!ctx || n < 0 || (n > 0 && (!xs || !ys))) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_set_points");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, d.xs.reserve((size_t)n * 8 + 64));
+        CU(ctx, d.ys.reserve((size_t)n * 8 + 64));
+        if (n) {
+            CU(ctx, cudaMemcpyAsync(d.xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMemcpyAsync(d.ys.p, ys, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+        }
+    }
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+    }
+    ctx->n_points = n;
+    return CLOSYR_OK;
+}
+
+int closyr_upload_population(closyr_ctx *ctx, const closyr_population *pop)
+{
+    if (!ctx) return CLOSYR_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    int rc = check_population(ctx, pop);
+    if (rc) return rc;
+    const int D = (int)ctx->devs.size();
+    const int64_t ne = pop->n_expr;
+    std::vector<int64_t> cut((size_t)D + 1, 0);
+    cut[(size_t)D] = ne;
+    if (ctx->flags & CLOSYR_SHARD_POINTS) {
+        for (int i = 1; i < D; i++) cut[(size_t)i] = 0;     // every device holds the whole population
+    } else if (ne > 0) {
+        // contiguous blocks balanced by program length (a proxy of the work per expression)
+        const uint64_t total = (uint64_t)(pop->code_off[ne] - pop->code_off[0]);
+        int64_t e = 0;
+        for (int i = 1; i < D; i++) {
+            const uint64_t want = total * (uint64_t)i / (uint64_t)D;
+            while (e < ne && (uint64_t)(pop->code_off[e] - pop->code_off[0]) < want) e++;
+            cut[(size_t)i] = e;
+        }
+    }
+    for (int i = 0; i < D; i++) {
+        DeviceState &d = ctx->devs[(size_t)i];
+        const bool all = (ctx->flags & CLOSYR_SHARD_POINTS) != 0;
+        rc = upload_shard(ctx, d, d.pop, pop, all ? 0 : cut[(size_t)i], all ? ne : cut[(size_t)i + 1]);
+        if (rc) return rc;
+        const int64_t n_here = d.pop.hi - d.pop.lo;
+        CU(ctx, d.scores.reserve((size_t)std::max<int64_t>(1, n_here) * 8));
+        CU(ctx, d.rflags.reserve((size_t)std::max<int64_t>(1, n_here)));
+    }
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaStreamSynchronize(d.stream));   // the caller's buffers may be reused after return
+    }
+    ctx->n_expr = ne;
+    ctx->scored = false;
+    return CLOSYR_OK;
+}
+
+int closyr_score_resident(closyr_ctx *ctx, int32_t max_leafs, float *device_ms)
+{
+    if (!ctx) return CLOSYR_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (ctx->n_points < 0) return fail(ctx, CLOSYR_E_STATE, "closyr_set_points has not been called");
+    if (ctx->n_expr < 0) return fail(ctx, CLOSYR_E_STATE, "no resident population");
+    const int D = (int)ctx->devs.size();
+    const int64_t nch = n_chunks_of(ctx->n_points);
+    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && D > 1;
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaEventRecord(d.ev0, d.stream));
+    }
+    if (!by_points) {
+        for (auto &d : ctx->devs) {
+            CU(ctx, cudaSetDevice(d.device));
+            int rc = launch_range(ctx, d, max_leafs, 0, nch, true, nullptr);
+            if (rc) return rc;
+        }
+    } else {
+        // aligned power-of-two chunk span per device; device 0 gathers one partial triple per expression
+        const int64_t span = pow2_ceil((nch + D - 1) / D);
+        DeviceState &d0 = ctx->devs[0];
+        const int64_t ne = ctx->n_expr;
+        CU(ctx, cudaSetDevice(d0.device));
+        CU(ctx, d0.partials_all.reserve((size_t)D * std::max<int64_t>(1, ne) * 3 * 8));
+        int parts = 0;
+        for (int i = 0; i < D; i++) {
+            DeviceState &d = ctx->devs[(size_t)i];
+            const int64_t lo = std::min(nch, (int64_t)i * span), hi = std::min(nch, lo + span);
+            d.chunk_lo = lo;
+            d.chunk_hi = hi;
+            if (hi <= lo) continue;
+            parts = i + 1;
+            CU(ctx, cudaSetDevice(d.device));
+            double *dst = nullptr;
+            if (i == 0) dst = (double *)d0.partials_all.p;
+            else {
+                CU(ctx, d.partials_all.reserve((size_t)std::max<int64_t>(1, ne) * 3 * 8));
+                dst = (double *)d.partials_all.p;
+            }
+            int rc = launch_range(ctx, d, max_leafs, lo, hi, false, dst);
+            if (rc) return rc;
+            CU(ctx, cudaEventRecord(d.done, d.stream));
+        }
+        CU(ctx, cudaSetDevice(d0.device));
+        for (int i = 1; i < parts; i++) {
+            DeviceState &d = ctx->devs[(size_t)i];
+            CU(ctx, cudaStreamWaitEvent(d0.stream, d.done, 0));
+            CU(ctx, cudaMemcpyPeerAsync((double *)d0.partials_all.p + (size_t)i * ne * 3, d0.device, d.partials_all.p,
+                                        d.device, (size_t)ne * 3 * 8, d0.stream));
+        }
+        if (ne > 0) {
+            FinalizeParams fp;
+            fp.meta = (const uint32_t *)d0.pop.meta.p;
+            fp.partials = (const double *)d0.partials_all.p;
+            fp.n_expr = ne;
+            fp.n_tiles_total = std::max(1, parts);
+            fp.max_leafs = max_leafs;
+            fp.n = ctx->n_points;
+            fp.scores = (double *)d0.scores.p;
+            fp.rflags = (uint8_t *)d0.rflags.p;
+            fp.out_partials = nullptr;
+            launch_finalize(fp, d0.stream);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+        }
+    }
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaEventRecord(d.ev1, d.stream));
+    }
+    float worst = 0.f;
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        worst = std::max(worst, ms);
+    }
+    if (device_ms) *device_ms = worst;
+    ctx->scored = true;
+    return CLOSYR_OK;
+}
+
+int closyr_download_scores(closyr_ctx *ctx, double *out_scores, uint8_t *out_flags)
+{
+    if (!ctx || !out_scores) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_download_scores");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (!ctx->scored) return fail(ctx, CLOSYR_E_STATE, "no scores: call closyr_score_resident first");
+    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && ctx->devs.size() > 1;
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+        DeviceState &d = ctx->devs[i];
+        if (by_points && i > 0) break;
+        const int64_t ne = d.pop.hi - d.pop.lo;
+        if (ne <= 0) continue;
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaMemcpyAsync(out_scores + d.pop.lo, d.scores.p, (size_t)ne * 8, cudaMemcpyDeviceToHost, d.stream));
+        if (out_flags) CU(ctx, cudaMemcpyAsync(out_flags + d.pop.lo, d.rflags.p, (size_t)ne, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return CLOSYR_OK;
+}
+
+int closyr_score_batch(closyr_ctx *ctx, const closyr_population *pop, int32_t max_leafs, double *out_scores,
+                       uint8_t *out_flags)
+{
+    int rc = closyr_upload_population(ctx, pop);
+    if (rc) return rc;
+    rc = closyr_score_resident(ctx, max_leafs, nullptr);
+    if (rc) return rc;
+    return closyr_download_scores(ctx, out_scores, out_flags);
+}
+
+int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const double *xs, int64_t n, double *out_f,
+                      uint8_t *out_status)
+{
+    if (!ctx || n < 0 || (n > 0 && (!xs || !out_f)) || !out_status) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_eval_batch");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    int rc = check_population(ctx, pop);
+    if (rc) return rc;
+    DeviceState &d = ctx->devs[0];
+    const int64_t ne = pop->n_expr;
+    if (ne == 0) return CLOSYR_OK;
+    rc = upload_shard(ctx, d, d.eval_pop, pop, 0, ne);
+    if (rc) return rc;
+    CU(ctx, d.eval_xs.reserve((size_t)n * 8 + 64));
+    CU(ctx, d.eval_f.reserve((size_t)std::max<int64_t>(1, ne * n) * 8));
+    CU(ctx, d.eval_status.reserve((size_t)ne));
+    if (n) CU(ctx, cudaMemcpyAsync(d.eval_xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+    EvalParams ep;
+    ep.pop = d.eval_pop.view();
+    ep.xs = (const double *)d.eval_xs.p;
+    ep.n = n;
+    ep.out_f = (double *)d.eval_f.p;
+    ep.status = (uint8_t *)d.eval_status.p;
+    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts), d.stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    if (n) CU(ctx, cudaMemcpyAsync(out_f, d.eval_f.p, (size_t)(ne * n) * 8, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(out_status, d.eval_status.p, (size_t)ne, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return CLOSYR_OK;
+}
+
+int closyr_score_partials_resident(closyr_ctx *ctx, int32_t max_leafs, int64_t chunk_begin, int64_t chunk_end,
+                                   void *dev_partials)
+{
+    if (!ctx || !dev_partials || chunk_begin < 0 || chunk_end < chunk_begin)
+        return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_score_partials_resident");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (ctx->n_points < 0) return fail(ctx, CLOSYR_E_STATE, "closyr_set_points has not been called");
+    if (ctx->n_expr < 0) return fail(ctx, CLOSYR_E_STATE, "no resident population");
+    const int64_t nch = n_chunks_of(ctx->n_points);
+    chunk_end = std::min(chunk_end, nch);
+    const int64_t span = pow2_ceil(std::max<int64_t>(1, chunk_end - chunk_begin));
+    if (chunk_begin % span != 0 && chunk_begin < chunk_end)
+        return fail(ctx, CLOSYR_E_ARG, "chunk range must be an aligned power-of-two span (fixed reduction tree)");
+    DeviceState &d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.device));
+    if (chunk_begin >= chunk_end) {
+        CU(ctx, cudaMemsetAsync(dev_partials, 0, (size_t)ctx->n_expr * 3 * 8, d.stream));
+    } else {
+        int rc = launch_range(ctx, d, max_leafs, chunk_begin, chunk_end, false, (double *)dev_partials);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return CLOSYR_OK;
+}
+
+int closyr_finalize_partials(closyr_ctx *ctx, const void *dev_partials_all, int n_parts, int32_t max_leafs)
+{
+    if (!ctx || !dev_partials_all || n_parts < 1) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_finalize_partials");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (ctx->n_expr < 0) return fail(ctx, CLOSYR_E_STATE, "no resident population");
+    DeviceState &d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.device));
+    if (ctx->n_expr > 0) {
+        FinalizeParams fp;
+        fp.meta = (const uint32_t *)d.pop.meta.p;
+        fp.partials = (const double *)dev_partials_all;
+        fp.n_expr = ctx->n_expr;
+        fp.n_tiles_total = n_parts;
+        fp.max_leafs = max_leafs;
+        fp.n = ctx->n_points;
+        fp.scores = (double *)d.scores.p;
+        fp.rflags = (uint8_t *)d.rflags.p;
+        fp.out_partials = nullptr;
+        launch_finalize(fp, d.stream);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    ctx->scored = true;
+    return CLOSYR_OK;
+}
+
+int closyr_score_from_values(closyr_ctx *ctx, const double *f, const double *ys, int64_t n, int32_t leafs, double *out3)
+{
+    if (!ctx || n < 0 || (n > 0 && (!f || !ys)) || !out3) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_score_from_values");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    DeviceState &d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.device));
+    CU(ctx, d.eval_f.reserve((size_t)(2 * n + 4) * 8));
+    double *df = (double *)d.eval_f.p, *dy = df + n, *dout = dy + n;
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(df, f, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(dy, ys, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+    }
+    launch_score_values(df, dy, n, leafs, dout, d.stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out3, dout, 3 * 8, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return CLOSYR_OK;
+}
+
+int closyr_rank_resident(closyr_ctx *ctx, int64_t k, int64_t *out_indices)
+{
+    if (!ctx || k < 0 || (k > 0 && !out_indices)) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_rank_resident");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (!ctx->scored) return fail(ctx, CLOSYR_E_STATE, "no scores: call closyr_score_resident first");
+    const int64_t ne = ctx->n_expr;
+    if (k > ne) k = ne;
+    if (k == 0) return CLOSYR_OK;
+    DeviceState &d0 = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d0.device));
+    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && ctx->devs.size() > 1;
+    const double *scores = (const double *)d0.scores.p;
+    if (ctx->devs.size() > 1 && !by_points) {
+        // gather every shard's scores on device 0 (peer copy over NVLink when available)
+        CU(ctx, d0.rank_b.reserve((size_t)ne * 8 + (size_t)k * 8));
+        for (auto &d : ctx->devs) {
+            const int64_t n_here = d.pop.hi - d.pop.lo;
+            if (n_here <= 0) continue;
+            CU(ctx, cudaMemcpyPeerAsync((double *)d0.rank_b.p + d.pop.lo, d0.device, d.scores.p, d.device,
+                                        (size_t)n_here * 8, d0.stream));
+        }
+        scores = (const double *)d0.rank_b.p;
+    } else CU(ctx, d0.rank_b.reserve((size_t)ne * 8 + (size_t)k * 8));
+    CU(ctx, d0.rank_a.reserve(rank_scratch_bytes(ne)));
+    int64_t *d_out = (int64_t *)((double *)d0.rank_b.p + ne);
+    ctx->launches += launch_rank(scores, ne, k, d0.rank_a.p, d_out, d0.stream);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out_indices, d_out, (size_t)k * 8, cudaMemcpyDeviceToHost, d0.stream));
+    CU(ctx, cudaStreamSynchronize(d0.stream));
+    return CLOSYR_OK;
+}
+
+int closyr_l2_flush(closyr_ctx *ctx)
+{
+    if (!ctx) return CLOSYR_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t bytes = (size_t)256 << 20;      // twice the 126 MB L2
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, d.flush.reserve(bytes));
+        CU(ctx, cudaMemsetAsync(d.flush.p, 0x5a, bytes, d.stream));
+    }
+    for (auto &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.device));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return CLOSYR_OK;
+}
+
+int closyr_fp64_peak_probe(closyr_ctx *ctx, double *dfma_per_second)
+{
+    if (!ctx || !dfma_per_second) return CLOSYR_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.device));
+    const int blocks = 148 * 8, iters = 20000;
+    CU(ctx, d.flush.reserve((size_t)blocks * 256 * 8));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(ctx, cudaEventRecord(d.ev0, d.stream));
+        launch_fp64_probe((double *)d.flush.p, iters, blocks, d.stream);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(d.ev1, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, rate);
+    }
+    *dfma_per_second = best;
+    return CLOSYR_OK;
+}
+
+int64_t closyr_kernel_launch_count(const closyr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *closyr_host_alloc(size_t bytes) { return pinned_alloc(bytes); }
+void closyr_host_free(void *p) { if (p) pinned_free(p); }
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// kernels.cu -- sm_100a kernels of the scoring path.
+//
+// score_kernel: one warp (= one CTA) per (expression, tile of points).  The program and its constant pool are
+// staged in shared memory; lanes stride over the points, 4 consecutive points per lane per pass (two 16-byte
+// loads of xs and of ys per lane, a warp reads 1 KiB contiguous); the residuals are reduced with a fixed-shape
+// tree (lane-local left fold of 4, xor-butterfly over the warp, index-aligned binary tree over 128-point
+// chunks) so a score is bit-identical for every tiling, sharding and GPU count.  The epilogue reproduces
+// closyr's formula operation by operation (reference src/closyr/ops.clj:78-116); the file is compiled with
+// -fmad=false so none of it is contracted.
+#include <cstdint>
+
+#include "kernels.cuh"
+#include "vm.cuh"
+
+namespace closyr {
+namespace {
+
+using namespace dev;
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_LEVELS = 40;
+
+__device__ __forceinline__ double warp_sum(double s)
+{
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) s = s + __shfl_xor_sync(FULL, s, st);
+    return s;
+}
+__device__ __forceinline__ double warp_max(double m)
+{
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, st));
+    return m;
+}
+
+// ops.clj:98-116 with the exact operation order; leafs is Symja's leafCount (ops.clj:127)
+__device__ __forceinline__ double score_formula(double sum, double mx, int64_t n, int leafs)
+{
+    const double mean = sum / (double)n;
+    const double score = -1.0 * ((2.0 * mean) + mx);
+    double pen = (0.0000001 * (double)leafs) * (double)leafs;
+    if (pen > 0.1) pen = 0.1;
+    const double ded = fabs(score) * pen;
+    return score - ded;
+}
+
+struct Staged {
+    const uint32_t *scode;
+    const double *sconst;
+    double *slvl;
+};
+
+// copies one program into shared memory: [constants | levels | code (+1 word of slack)]
+__device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int lane)
+{
+    const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
+    const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
+    const uint32_t ncode = c1 - c0, nk = k1 - k0;
+    double *sconst = reinterpret_cast<double *>(smem);
+    double *slvl = sconst + nk;
+    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + MAX_LEVELS);
+    const double *gk = pop.consts + (k0 - pop.const_base);
+    const uint32_t *gc = pop.code + (c0 - pop.code_base);
+    for (uint32_t i = lane; i < nk; i += 32) sconst[i] = gk[i];
+    for (uint32_t i = lane; i < ncode; i += 32) scode[i] = gc[i];
+    if (lane == 0) scode[ncode] = 0;
+    __syncwarp();
+    Staged s = { scode, sconst, slvl };
+    return s;
+}
+
+// evaluates one 128-point chunk: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points whose value is
+// not a real number (eval.clj:70-80 turns those into +Inf).  Returns true when full semantics were needed.
+__device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool quirk, uint32_t quirk_off, int64_t base,
+                                           int64_t n, const double *__restrict__ xs, double (&x)[4], double (&v)[4],
+                                           uint32_t &valid, uint32_t &nr)
+{
+    valid = 0;
+    nr = 0;
+    if (base + 3 < n) {
+        const double2 a = *reinterpret_cast<const double2 *>(xs + base);
+        const double2 b = *reinterpret_cast<const double2 *>(xs + base + 2);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+        valid = 0xfu;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool ok = base + j < n;
+            x[j] = ok ? xs[base + j] : 1.0;
+            valid |= (ok ? 1u : 0u) << j;
+        }
+    }
+    if (quirk) {
+        // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
+        return false;
+    }
+    uint32_t ev = run_real<4>(st.scode, st.sconst, x, v);
+    if (is_const) ev = 0xfu;
+    ev &= valid;
+    if (!__any_sync(FULL, ev != 0)) return false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if ((ev >> j) & 1u) {
+            const Z z = full_eval(st.scode, st.sconst, x[j]);
+            if (ztag(z) == T_REAL) v[j] = z.re;
+            else { v[j] = 0.0; nr |= 1u << j; }
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t item = blockIdx.x;
+    const int64_t e = item / p.n_tiles;
+    const int tile = (int)(item - e * p.n_tiles);
+    const uint32_t meta = p.pop.meta[e];
+    const int leafs = (int)(meta & 0xffffu);
+    const uint32_t flags = (meta >> 16) & 0xffu;
+
+    const bool too_big = leafs > p.max_leafs;                               // ops.clj:128-129
+    const bool dead = (flags & (CL_F_UNSUPPORTED | CL_F_NIL)) != 0;        // eval nil / unsupported => min-score
+    if (too_big || dead || p.n <= 0) {
+        if (lane == 0) {
+            if (p.final_scores) {
+                p.scores[e] = CLOSYR_MIN_SCORE;
+                p.rflags[e] = too_big ? CL_R_TOO_BIG : CL_R_MIN_SCORE;
+            } else {
+                double *out = p.partials + ((p.partial_tile_offset + tile) * p.pop.n_expr + e) * 3;
+                out[0] = 0.0; out[1] = 0.0; out[2] = 0.0;
+            }
+        }
+        return;
+    }
+
+    const Staged st = stage_program(p.pop, e, smem, lane);
+    const bool is_const = (flags & CL_F_CONST) != 0;
+    const uint32_t aux = p.pop.aux[e];
+    const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
+    const uint32_t quirk_off = aux & 0xffffu;
+
+    const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
+    int64_t c_hi = c_lo + p.chunks_per_tile;
+    if (c_hi > p.chunk_end) c_hi = p.chunk_end;
+
+    double tile_max = 0.0;
+    uint32_t nonreal = 0;
+    bool used_full = false;
+    uint32_t cnt = 0;
+    for (int64_t c = c_lo; c < c_hi; c++, cnt++) {
+        const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        double x[4], v[4], y[4];
+        uint32_t valid, nr;
+        used_full |= eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr);
+        if (base + 3 < p.n) {
+            const double2 a = *reinterpret_cast<const double2 *>(p.ys + base);
+            const double2 b = *reinterpret_cast<const double2 *>(p.ys + base + 2);
+            y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] = (base + j < p.n) ? p.ys[base + j] : 0.0;
+        }
+        // compute-residual (ops.clj:78-90): NaN or non-real => max-resid; else min(max-resid, |y - f|)
+        double s = 0.0, m = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double r = fmin(CLOSYR_MAX_RESID, fabs(y[j] - v[j]));
+            if ((nr >> j) & 1u) r = CLOSYR_MAX_RESID;
+            if (!((valid >> j) & 1u)) r = 0.0;
+            s = s + r;
+            m = fmax(m, r);
+        }
+        nonreal += __popc(nr);
+        s = warp_sum(s);
+        tile_max = fmax(tile_max, m);
+        // streaming pairwise insertion: level k holds the sum of an aligned block of 2^k chunks
+        uint32_t k = 0;
+        for (uint32_t t = cnt; t & 1u; t >>= 1, k++) s = st.slvl[k] + s;
+        __syncwarp();
+        if (lane == 0) st.slvl[k] = s;
+        __syncwarp();
+    }
+    double tile_sum = 0.0;
+    bool have = false;
+    for (uint32_t k = 0; (cnt >> k) != 0; k++) {
+        if ((cnt >> k) & 1u) {
+            tile_sum = have ? st.slvl[k] + tile_sum : st.slvl[k];
+            have = true;
+        }
+    }
+    tile_max = warp_max(tile_max);
+    nonreal = __reduce_add_sync(FULL, nonreal);
+
+    if (lane != 0) return;
+    if (p.final_scores) {
+        uint8_t rf = used_full ? CL_R_FULL_SEMANTICS : 0;
+        double score;
+        if (is_const && !quirk && nonreal != 0) {                     // eval.clj:83-96 throws => min-score
+            score = CLOSYR_MIN_SCORE;
+            rf |= CL_R_MIN_SCORE;
+        } else score = score_formula(tile_sum, tile_max, p.n, leafs);
+        p.scores[e] = score;
+        p.rflags[e] = rf;
+    } else {
+        double *out = p.partials + ((p.partial_tile_offset + tile) * p.pop.n_expr + e) * 3;
+        out[0] = tile_sum;
+        out[1] = tile_max;
+        out[2] = (double)nonreal + (used_full ? 0.25 : 0.0);          // fraction carries the diagnostic bit
+    }
+}
+
+// combines per-tile partials in global tile order with the same aligned binary tree, then the epilogue
+__global__ void finalize_kernel(const FinalizeParams p)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_expr) return;
+    const uint32_t meta = p.meta[e];
+    const int leafs = (int)(meta & 0xffffu);
+    const uint32_t flags = (meta >> 16) & 0xffu;
+    if (!p.out_partials) {
+        if (leafs > p.max_leafs) { p.scores[e] = CLOSYR_MIN_SCORE; p.rflags[e] = CL_R_TOO_BIG; return; }
+        if ((flags & (CL_F_UNSUPPORTED | CL_F_NIL)) || p.n <= 0) { p.scores[e] = CLOSYR_MIN_SCORE; p.rflags[e] = CL_R_MIN_SCORE; return; }
+    }
+    double lvl[32];
+    double mx = 0.0, nonreal = 0.0;
+    bool used_full = false;
+    for (int t = 0; t < p.n_tiles_total; t++) {
+        const double *in = p.partials + ((int64_t)t * p.n_expr + e) * 3;
+        double s = in[0];
+        mx = fmax(mx, in[1]);
+        const double nr = floor(in[2]);
+        used_full |= in[2] != nr;
+        nonreal += nr;
+        int k = 0;
+        for (uint32_t c = (uint32_t)t; c & 1u; c >>= 1, k++) s = lvl[k] + s;
+        lvl[k] = s;
+    }
+    double sum = 0.0;
+    bool have = false;
+    for (int k = 0; ((uint32_t)p.n_tiles_total >> k) != 0; k++) {
+        if (((uint32_t)p.n_tiles_total >> k) & 1u) {
+            sum = have ? lvl[k] + sum : lvl[k];
+            have = true;
+        }
+    }
+    if (p.out_partials) {
+        double *out = p.out_partials + e * 3;
+        out[0] = sum;
+        out[1] = mx;
+        out[2] = nonreal + (used_full ? 0.25 : 0.0);
+        return;
+    }
+    uint8_t rf = used_full ? CL_R_FULL_SEMANTICS : 0;
+    double score;
+    if ((flags & CL_F_CONST) && nonreal != 0.0) { score = CLOSYR_MIN_SCORE; rf |= CL_R_MIN_SCORE; }
+    else score = score_formula(sum, mx, p.n, leafs);
+    p.scores[e] = score;
+    p.rflags[e] = rf;
+}
+
+// eval-vec-pheno for a batch (eval.clj:99-112): out_f[e][i] = real value or +Inf; status 0 ok, 1 nil, 2 throws
+__global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t e = blockIdx.x;
+    const uint32_t meta = p.pop.meta[e];
+    const uint32_t flags = (meta >> 16) & 0xffu;
+    if (flags & (CL_F_UNSUPPORTED | CL_F_NIL)) {
+        if (lane == 0) p.status[e] = 1;
+        return;
+    }
+    const Staged st = stage_program(p.pop, e, smem, lane);
+    const bool is_const = (flags & CL_F_CONST) != 0;
+    const uint32_t aux = p.pop.aux[e];
+    const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
+    const uint32_t quirk_off = aux & 0xffffu;
+    const int64_t nchunks = (p.n + CHUNK_POINTS - 1) / CHUNK_POINTS;
+    uint32_t nonreal = 0;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        double x[4], v[4];
+        uint32_t valid, nr;
+        eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr);
+        nonreal += __popc(nr);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((valid >> j) & 1u) p.out_f[e * p.n + base + j] = ((nr >> j) & 1u) ? inf : v[j];
+    }
+    nonreal = __reduce_add_sync(FULL, nonreal);
+    if (lane == 0) p.status[e] = (is_const && !quirk && nonreal != 0) ? 2 : 0;
+}
+
+// compute-score-from-actuals-and-expecteds (ops.clj:98-116) on given f values: one warp, same reduction tree
+__global__ void __launch_bounds__(32) score_values_kernel(const double *f, const double *ys, int64_t n, int32_t leafs,
+                                                          double *out3)
+{
+    __shared__ double slvl[MAX_LEVELS];
+    const int lane = threadIdx.x;
+    const int64_t nchunks = (n + CHUNK_POINTS - 1) / CHUNK_POINTS;
+    double mx = 0.0;
+    uint32_t cnt = 0;
+    for (int64_t c = 0; c < nchunks; c++, cnt++) {
+        const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double r = 0.0;
+            if (base + j < n) {
+                const double actual = f[base + j];
+                r = (actual != actual) ? CLOSYR_MAX_RESID : fmin(CLOSYR_MAX_RESID, fabs(ys[base + j] - actual));
+            }
+            s = s + r;
+            mx = fmax(mx, r);
+        }
+        s = warp_sum(s);
+        uint32_t k = 0;
+        for (uint32_t t = cnt; t & 1u; t >>= 1, k++) s = slvl[k] + s;
+        __syncwarp();
+        if (lane == 0) slvl[k] = s;
+        __syncwarp();
+    }
+    double sum = 0.0;
+    bool have = false;
+    for (uint32_t k = 0; (cnt >> k) != 0; k++)
+        if ((cnt >> k) & 1u) { sum = have ? slvl[k] + sum : slvl[k]; have = true; }
+    mx = warp_max(mx);
+    if (lane == 0) {
+        out3[0] = n > 0 ? score_formula(sum, mx, n, leafs) : CLOSYR_MIN_SCORE;
+        out3[1] = sum;
+        out3[2] = mx;
+    }
+}
+
+// register-resident DFMA chains: the measured denominator of the FP64 roofline
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+    const double b = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
+{
+    const int64_t items = p.pop.n_expr * p.n_tiles;
+    if (items <= 0) return;
+    score_kernel<<<(unsigned)items, 32, smem_bytes, (cudaStream_t)stream>>>(p);
+}
+
+void launch_finalize(const FinalizeParams &p, void *stream)
+{
+    if (p.n_expr <= 0) return;
+    const int threads = 128;
+    finalize_kernel<<<(unsigned)((p.n_expr + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_eval(const EvalParams &p, size_t smem_bytes, void *stream)
+{
+    if (p.pop.n_expr <= 0) return;
+    eval_kernel<<<(unsigned)p.pop.n_expr, 32, smem_bytes, (cudaStream_t)stream>>>(p);
+}
+
+void launch_score_values(const double *f, const double *ys, int64_t n, int32_t leafs, double *out3, void *stream)
+{
+    score_values_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, ys, n, leafs, out3);
+}
+
+void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
+{
+    fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
+}
+
+size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts)
+{
+    return (size_t)max_consts * 8 + MAX_LEVELS * 8 + ((size_t)max_code_words + 1) * 4 + 16;
+}
+
+}  // namespace closyr

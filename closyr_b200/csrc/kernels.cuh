@@ -1,0 +1,65 @@
+// kernels.cuh -- launch parameters shared by kernels.cu and ctx.cu
+#pragma once
+#include <cstdint>
+
+namespace closyr {
+
+constexpr int CHUNK_POINTS = 128;     // 32 lanes x 4 consecutive points: the leaf of the fixed reduction tree
+constexpr int POINTS_PER_LANE = 4;
+
+struct DevPopulation {                // device pointers of one resident shard
+    const uint32_t *code;
+    const uint32_t *code_off;         // [n_expr + 1], absolute word offsets of the caller's buffer
+    const double *consts;
+    const uint32_t *const_off;        // [n_expr + 1]
+    const uint32_t *meta;
+    const uint32_t *aux;
+    uint32_t code_base;               // code_off value of the shard's first expression
+    uint32_t const_base;
+    int64_t n_expr;
+};
+
+struct ScoreParams {
+    DevPopulation pop;
+    const double *xs;
+    const double *ys;
+    int64_t n;                        // total number of points of the run
+    int64_t chunk_begin, chunk_end;   // 128-point chunks [begin, end) evaluated by this launch
+    int32_t chunks_per_tile;          // power of two; one warp reduces one tile
+    int32_t n_tiles;                  // tiles per expression in this launch
+    int32_t max_leafs;
+    int32_t final_scores;             // 1: one tile covers every point -> write scores; 0: write partials
+    double *scores;                   // [n_expr]
+    uint8_t *rflags;                  // [n_expr]
+    double *partials;                 // [n_tiles][n_expr][3] = sum, max, non-real count
+    int64_t partial_tile_offset;      // index of this launch's first tile inside `partials`
+};
+
+struct FinalizeParams {
+    const uint32_t *meta;
+    const double *partials;           // [n_tiles_total][n_expr][3]
+    int64_t n_expr;
+    int32_t n_tiles_total;
+    int32_t max_leafs;
+    int64_t n;
+    double *scores;
+    uint8_t *rflags;
+    double *out_partials;             // non-NULL: emit one combined triple per expression instead of a score
+};
+
+struct EvalParams {
+    DevPopulation pop;
+    const double *xs;
+    int64_t n;
+    double *out_f;                    // [n_expr][n]
+    uint8_t *status;                  // [n_expr]
+};
+
+void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream);
+void launch_finalize(const FinalizeParams &p, void *stream);
+void launch_eval(const EvalParams &p, size_t smem_bytes, void *stream);
+void launch_score_values(const double *f, const double *ys, int64_t n, int32_t leafs, double *out3, void *stream);
+void launch_fp64_probe(double *out, int iters, int blocks, void *stream);
+size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts);
+
+}  // namespace closyr

@@ -1,0 +1,445 @@
+// vm.cuh -- device-side bytecode interpreters for sm_100a.
+//
+// Two evaluators share one ISA (include/closyr_b200.h):
+//   * run_real<P>:  the fast path.  IEEE-754 fp64 on P points per lane, accumulator and spill slots 0..3 in
+//                   registers, every lane of the warp runs the same program so the dispatch branch is uniform.
+//                   It is exact whenever the evaluation stays on the real line; it reports (per point) when
+//                   it cannot know that: the result is NaN, or an instruction met a case where Symja's value
+//                   algebra differs observably from IEEE (E^(-Infinity) vs E^ComplexInfinity, literals that are
+//                   not real, general x^y).
+//   * full_eval:    the complete value algebra of the scoring path (reals, complex numbers, ComplexInfinity,
+//                   Indeterminate; SURVEY.md Appendix A, DESIGN.md "Semantics"), one point per lane.  Only the
+//                   128-point chunks in which some point raised the report above are re-evaluated with it.
+// What is being replaced: Symja's ExprEvaluator.eval of Function({x},expr)[List(xs)]
+// (reference src/closyr/ops/eval.clj:40-56) and the per-element decode (eval.clj:70-80).
+#pragma once
+#include <cstdint>
+
+#include "../../include/closyr_b200.h"
+
+namespace closyr {
+namespace dev {
+
+// ------------------------------------------------------------------------------------------------
+// real line helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nonfinite(double x) { return (__double2hiint(x) & 0x7ff00000) == 0x7ff00000; }
+__device__ __forceinline__ bool is_neg_inf(double x)
+{
+    return __double2hiint(x) == (int)0xfff00000 && __double2loint(x) == 0;
+}
+__device__ __forceinline__ bool is_integer_value(double y) { return !nonfinite(y) && floor(y) == y; }
+
+// integer power by square-and-multiply, MSB first (the same chain the oracle walks)
+__device__ __forceinline__ double powi_real(double a, int n)
+{
+    unsigned m = (unsigned)(n < 0 ? -n : n);
+    int top = 31 - __clz((int)m);
+    double r = a;
+    for (int b = top - 1; b >= 0; b--) {
+        r = r * r;
+        if ((m >> b) & 1u) r = r * a;
+    }
+    return n < 0 ? 1.0 / r : r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// full value algebra
+// ------------------------------------------------------------------------------------------------
+struct Z { double re, im; };
+enum { T_REAL = 0, T_CPLX = 1, T_CINF = 2, T_INDET = 3 };
+
+__device__ __forceinline__ int ztag(Z v)
+{
+    if (isnan(v.re) || isnan(v.im)) return T_INDET;
+    if (v.im == 0.0) return T_REAL;
+    if (isinf(v.re) || isinf(v.im)) return T_CINF;
+    return T_CPLX;
+}
+__device__ __forceinline__ Z zv(double re, double im) { Z z; z.re = re; z.im = im; return z; }
+__device__ __forceinline__ Z zindet() { return zv(__longlong_as_double(0x7ff8000000000000ll), 0.0); }
+__device__ __forceinline__ Z zcinf() { return zv(__longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0x7ff0000000000000ll)); }
+__device__ __forceinline__ Z zmk(double re, double im)
+{
+    Z v = zv(re, im);
+    int t = ztag(v);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zcinf();
+    if (t == T_REAL) return zv(re, 0.0);
+    return v;
+}
+
+__device__ __noinline__ Z zadd(Z a, Z b)
+{
+    int ta = ztag(a), tb = ztag(b);
+    if (ta == T_INDET || tb == T_INDET) return zindet();
+    if (ta == T_CINF || tb == T_CINF) {
+        Z o = (ta == T_CINF) ? b : a;
+        int to = (ta == T_CINF) ? tb : ta;
+        if (to == T_CINF) return zindet();
+        if (to == T_REAL && isinf(o.re)) return zindet();
+        return zcinf();
+    }
+    return zmk(a.re + b.re, a.im + b.im);
+}
+
+__device__ __noinline__ Z zmul(Z a, Z b)
+{
+    int ta = ztag(a), tb = ztag(b);
+    if (ta == T_INDET || tb == T_INDET) return zindet();
+    if (ta == T_CINF || tb == T_CINF) {
+        Z o = (ta == T_CINF) ? b : a;
+        int to = (ta == T_CINF) ? tb : ta;
+        if (to == T_REAL && o.re == 0.0) return zindet();
+        return zcinf();
+    }
+    if (ta == T_REAL && tb == T_REAL) return zmk(a.re * b.re, 0.0);
+    if (ta == T_REAL) return zmk(a.re * b.re, a.re * b.im);
+    if (tb == T_REAL) return zmk(a.re * b.re, a.im * b.re);
+    return zmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+
+__device__ __forceinline__ Z zneg(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zcinf();
+    if (t == T_REAL) return zv(-a.re, 0.0);
+    return zv(-a.re, -a.im);
+}
+
+__device__ __noinline__ Z zrecip(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zv(0.0, 0.0);
+    if (t == T_REAL) {
+        if (a.re == 0.0) return zcinf();
+        return zv(1.0 / a.re, 0.0);
+    }
+    double c = a.re, d = a.im;           // Smith's algorithm (Hipparchus Complex.reciprocal)
+    if (fabs(c) < fabs(d)) {
+        double q = c / d;
+        double s = 1.0 / (c * q + d);
+        return zmk(s * q, -s);
+    }
+    double q = d / c;
+    double s = 1.0 / (d * q + c);
+    return zmk(s, -s * q);
+}
+
+__device__ __noinline__ Z zsqrt(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zcinf();
+    if (t == T_REAL) {
+        if (a.re >= 0.0) return zv(sqrt(a.re), 0.0);
+        if (isinf(a.re)) return zcinf();
+        return zmk(0.0, sqrt(-a.re));
+    }
+    double x = a.re, y = a.im;
+    double tt = sqrt((fabs(x) + hypot(x, y)) / 2.0);
+    if (x >= 0.0) return zmk(tt, y / (2.0 * tt));
+    return zmk(fabs(y) / (2.0 * tt), copysign(tt, y));
+}
+
+__device__ __noinline__ Z zexp(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET || t == T_CINF) return zindet();
+    if (t == T_REAL) return zmk(exp(a.re), 0.0);
+    double e = exp(a.re);
+    return zmk(e * cos(a.im), e * sin(a.im));
+}
+
+__device__ __noinline__ Z zlog(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zv(__longlong_as_double(0x7ff0000000000000ll), 0.0);
+    if (t == T_REAL) {
+        if (a.re > 0.0) return zv(log(a.re), 0.0);
+        if (a.re == 0.0) return zv(__longlong_as_double(0xfff0000000000000ll), 0.0);
+        if (isinf(a.re)) return zcinf();
+        return zmk(log(-a.re), 3.141592653589793);
+    }
+    return zmk(log(hypot(a.re, a.im)), atan2(a.im, a.re));
+}
+
+__device__ __noinline__ Z zsin(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET || t == T_CINF) return zindet();
+    if (t == T_REAL) return zmk(sin(a.re), 0.0);
+    return zmk(sin(a.re) * cosh(a.im), cos(a.re) * sinh(a.im));
+}
+
+__device__ __noinline__ Z zcos(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET || t == T_CINF) return zindet();
+    if (t == T_REAL) return zmk(cos(a.re), 0.0);
+    return zmk(cos(a.re) * cosh(a.im), -(sin(a.re) * sinh(a.im)));
+}
+
+__device__ __noinline__ Z ztan(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET || t == T_CINF) return zindet();
+    if (t == T_REAL) return zmk(tan(a.re), 0.0);
+    if (a.im > 20.0) return zv(0.0, 1.0);
+    if (a.im < -20.0) return zv(0.0, -1.0);
+    double a2 = 2.0 * a.re, b2 = 2.0 * a.im;
+    double d = cos(a2) + cosh(b2);
+    return zmk(sin(a2) / d, sinh(b2) / d);
+}
+
+__device__ __forceinline__ Z zmul_i(Z a) { return zmk(-a.im, a.re); }
+__device__ __forceinline__ Z zmul_minus_i(Z a) { return zmk(a.im, -a.re); }
+__device__ __forceinline__ Z zsqrt1z(Z z) { return zsqrt(zadd(zv(1.0, 0.0), zneg(zmul(z, z)))); }
+
+__device__ __noinline__ Z zasin(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zcinf();
+    if (t == T_REAL) {
+        if (fabs(a.re) <= 1.0) return zv(asin(a.re), 0.0);
+        if (isinf(a.re)) return zcinf();
+    }
+    Z w = zlog(zadd(zsqrt1z(a), zmul_i(a)));
+    int tw = ztag(w);
+    if (tw == T_INDET) return zindet();
+    if (tw == T_CINF || (tw == T_REAL && isinf(w.re))) return zcinf();
+    return zmul_minus_i(w);
+}
+
+__device__ __noinline__ Z zacos(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zcinf();
+    if (t == T_REAL) {
+        if (fabs(a.re) <= 1.0) return zv(acos(a.re), 0.0);
+        if (isinf(a.re)) return zcinf();
+    }
+    Z s = zsqrt1z(a);
+    int ts = ztag(s);
+    if (ts == T_INDET) return zindet();
+    if (ts == T_CINF || (ts == T_REAL && isinf(s.re))) return zcinf();
+    Z w = zlog(zadd(a, zmul_i(s)));
+    int tw = ztag(w);
+    if (tw == T_INDET) return zindet();
+    if (tw == T_CINF || (tw == T_REAL && isinf(w.re))) return zcinf();
+    return zmul_minus_i(w);
+}
+
+__device__ __forceinline__ Z zabs(Z a)
+{
+    int t = ztag(a);
+    if (t == T_INDET) return zindet();
+    if (t == T_CINF) return zv(__longlong_as_double(0x7ff0000000000000ll), 0.0);
+    if (t == T_REAL) return zv(fabs(a.re), 0.0);
+    return zmk(hypot(a.re, a.im), 0.0);
+}
+
+__device__ __noinline__ Z zpowi(Z a, int n)
+{
+    unsigned m = (unsigned)(n < 0 ? -n : n);
+    int top = 31 - __clz((int)m);
+    Z r = a;
+    for (int b = top - 1; b >= 0; b--) {
+        r = zmul(r, r);
+        if ((m >> b) & 1u) r = zmul(r, a);
+    }
+    if (n < 0) r = zrecip(r);
+    return r;
+}
+
+__device__ __noinline__ Z zpow(Z z, Z w)
+{
+    const double PINF = __longlong_as_double(0x7ff0000000000000ll);
+    int tz = ztag(z), tw = ztag(w);
+    if (tz == T_INDET || tw == T_INDET) return zindet();
+    if (tw == T_CINF) return zindet();
+    double yr = w.re;
+    if (tz == T_CINF) {
+        if (tw == T_REAL && isinf(yr)) return zindet();
+        if (yr > 0.0) return zcinf();
+        if (yr < 0.0) return zv(0.0, 0.0);
+        return zindet();
+    }
+    if (tz == T_REAL && tw == T_REAL) {
+        double x = z.re, y = yr;
+        if (y == 0.0) return (!nonfinite(x) && x != 0.0) ? zv(1.0, 0.0) : zindet();
+        if (isinf(y)) {
+            double ax = fabs(x);
+            if (ax == 1.0) return zindet();
+            bool grows = (ax > 1.0) == (y > 0.0);
+            if (!grows) return zv(0.0, 0.0);
+            return (x > 0.0) ? zv(PINF, 0.0) : zcinf();
+        }
+        if (isinf(x)) {
+            if (y < 0.0) return zv(0.0, 0.0);
+            if (x > 0.0) return zv(PINF, 0.0);
+            return is_integer_value(y) ? zmk(pow(x, y), 0.0) : zcinf();
+        }
+        if (x == 0.0) return (y > 0.0) ? zv(0.0, 0.0) : zcinf();
+        if (x > 0.0 || is_integer_value(y)) return zmk(pow(x, y), 0.0);
+        double m = pow(-x, y);
+        double th = y * 3.141592653589793;
+        return zmk(m * cos(th), m * sin(th));
+    }
+    if (tz == T_REAL && z.re == 0.0) {
+        if (yr > 0.0) return zv(0.0, 0.0);
+        if (yr < 0.0) return zcinf();
+        return zindet();
+    }
+    if (tz == T_REAL && isinf(z.re)) {
+        if (yr > 0.0) return zcinf();
+        if (yr < 0.0) return zv(0.0, 0.0);
+        return zindet();
+    }
+    if (tw == T_REAL && isinf(yr)) {
+        double az = hypot(z.re, z.im);
+        if (az == 1.0) return zindet();
+        return ((az > 1.0) == (yr > 0.0)) ? zcinf() : zv(0.0, 0.0);
+    }
+    return zexp(zmul(w, zlog(z)));
+}
+
+// One point through the program with the complete value algebra.  Slots live in local memory.
+__device__ __noinline__ Z full_eval(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x)
+{
+    Z slot[CLOSYR_MAX_SLOTS];
+    Z acc = zv(0.0, 0.0);
+    const Z zx = zmk(x, 0.0);
+    for (int pc = 0;; pc++) {
+        const uint32_t w = scode[pc];
+        const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
+        const int b = (int)(w >> 16);
+        switch (op) {
+        case CL_END: return acc;
+        case CL_LDX: acc = zx; break;
+        case CL_LDC: acc = zmk(sconst[b], 0.0); break;
+        case CL_LDZ: acc = zmk(sconst[b], sconst[b + 1]); break;
+        case CL_LDSPEC: acc = a == 0 ? zcinf() : zindet(); break;
+        case CL_ADDX: acc = zadd(acc, zx); break;
+        case CL_ADDC: acc = zadd(acc, zmk(sconst[b], 0.0)); break;
+        case CL_MULX: acc = zmul(acc, zx); break;
+        case CL_MULC: acc = zmul(acc, zmk(sconst[b], 0.0)); break;
+        case CL_NEG: acc = zneg(acc); break;
+        case CL_RECIP: acc = zrecip(acc); break;
+        case CL_SQR: acc = zmul(acc, acc); break;
+        case CL_SQRT: acc = zsqrt(acc); break;
+        case CL_RSQRT: acc = zrecip(zsqrt(acc)); break;
+        case CL_POWI: acc = zpowi(acc, (int)(short)b); break;
+        case CL_POWC: acc = zpow(acc, zmk(sconst[b], 0.0)); break;
+        case CL_EXP: acc = zexp(acc); break;
+        case CL_LOG: acc = zlog(acc); break;
+        case CL_SIN: acc = zsin(acc); break;
+        case CL_COS: acc = zcos(acc); break;
+        case CL_TAN: acc = ztan(acc); break;
+        case CL_ASIN: acc = zasin(acc); break;
+        case CL_ACOS: acc = zacos(acc); break;
+        case CL_ABS: acc = zabs(acc); break;
+        case CL_POWS: acc = zpow(slot[a], acc); break;
+        default:
+            if (op >= CL_MULS0 || op == CL_MULS) acc = zmul(slot[a], acc);
+            else if (op >= CL_ADDS0 || op == CL_ADDS) acc = zadd(slot[a], acc);
+            else slot[a] = acc;     // CL_ST, CL_ST0..3
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: P points per lane, IEEE real arithmetic, register-resident accumulator and slots 0..3.
+// Returns a bit mask (bit j = point j) of points that must be re-evaluated by full_eval.
+// ------------------------------------------------------------------------------------------------
+#define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
+
+template <int P>
+__device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
+                                             const double (&x)[P], double (&acc)[P])
+{
+    double s0[P], s1[P], s2[P], s3[P];
+    double ls[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];    // deep spill slots: local memory, rarely touched
+    uint32_t ev = 0;
+    int pc = 0;
+    uint32_t w = scode[0];
+    CLOSYR_FORJ { acc[j] = 0.0; s0[j] = 0.0; s1[j] = 0.0; s2[j] = 0.0; s3[j] = 0.0; }
+    for (;;) {
+        const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
+        const int b = (int)(w >> 16);
+        w = scode[++pc];                                     // prefetch (the buffer has one word of slack)
+        switch (op) {
+        case CL_END: {
+            CLOSYR_FORJ if (acc[j] != acc[j]) ev |= 1u << j;
+            return ev;
+        }
+        case CL_LDX: CLOSYR_FORJ acc[j] = x[j]; break;
+        case CL_LDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = c; break; }
+        case CL_LDZ:
+        case CL_LDSPEC: ev = (1u << P) - 1u; break;
+        case CL_ADDX: CLOSYR_FORJ acc[j] = acc[j] + x[j]; break;
+        case CL_ADDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] + c; break; }
+        case CL_MULX: CLOSYR_FORJ acc[j] = acc[j] * x[j]; break;
+        case CL_MULC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] * c; break; }
+        case CL_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;
+        case CL_RECIP: CLOSYR_FORJ acc[j] = 1.0 / acc[j]; break;
+        case CL_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
+        case CL_SQRT: CLOSYR_FORJ acc[j] = sqrt(acc[j]); break;
+        case CL_RSQRT: CLOSYR_FORJ acc[j] = 1.0 / sqrt(acc[j]); break;
+        case CL_POWI: { const int n = (int)(short)b; CLOSYR_FORJ acc[j] = powi_real(acc[j], n); break; }
+        case CL_POWC: {
+            const double y = sconst[b];
+            if (nonfinite(y) || y == 0.0) { ev = (1u << P) - 1u; break; }
+            CLOSYR_FORJ acc[j] = pow(acc[j], y);
+            break;
+        }
+        case CL_EXP:
+            CLOSYR_FORJ { if (is_neg_inf(acc[j])) ev |= 1u << j; acc[j] = exp(acc[j]); }
+            break;
+        case CL_LOG: CLOSYR_FORJ acc[j] = log(acc[j]); break;
+        case CL_SIN: CLOSYR_FORJ acc[j] = sin(acc[j]); break;
+        case CL_COS: CLOSYR_FORJ acc[j] = cos(acc[j]); break;
+        case CL_TAN: CLOSYR_FORJ acc[j] = tan(acc[j]); break;
+        case CL_ASIN: CLOSYR_FORJ acc[j] = asin(acc[j]); break;
+        case CL_ACOS: CLOSYR_FORJ acc[j] = acos(acc[j]); break;
+        case CL_ABS: CLOSYR_FORJ acc[j] = fabs(acc[j]); break;
+        case CL_ST0 + 0: CLOSYR_FORJ s0[j] = acc[j]; break;
+        case CL_ST0 + 1: CLOSYR_FORJ s1[j] = acc[j]; break;
+        case CL_ST0 + 2: CLOSYR_FORJ s2[j] = acc[j]; break;
+        case CL_ST0 + 3: CLOSYR_FORJ s3[j] = acc[j]; break;
+        case CL_ADDS0 + 0: CLOSYR_FORJ acc[j] = s0[j] + acc[j]; break;
+        case CL_ADDS0 + 1: CLOSYR_FORJ acc[j] = s1[j] + acc[j]; break;
+        case CL_ADDS0 + 2: CLOSYR_FORJ acc[j] = s2[j] + acc[j]; break;
+        case CL_ADDS0 + 3: CLOSYR_FORJ acc[j] = s3[j] + acc[j]; break;
+        case CL_MULS0 + 0: CLOSYR_FORJ acc[j] = s0[j] * acc[j]; break;
+        case CL_MULS0 + 1: CLOSYR_FORJ acc[j] = s1[j] * acc[j]; break;
+        case CL_MULS0 + 2: CLOSYR_FORJ acc[j] = s2[j] * acc[j]; break;
+        case CL_MULS0 + 3: CLOSYR_FORJ acc[j] = s3[j] * acc[j]; break;
+        case CL_ST:
+            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ ls[a - CLOSYR_REG_SLOTS][j] = acc[j]; }
+            else ev = (1u << P) - 1u;
+            break;
+        case CL_ADDS:
+            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ acc[j] = ls[a - CLOSYR_REG_SLOTS][j] + acc[j]; }
+            else ev = (1u << P) - 1u;
+            break;
+        case CL_MULS:
+            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ acc[j] = ls[a - CLOSYR_REG_SLOTS][j] * acc[j]; }
+            else ev = (1u << P) - 1u;
+            break;
+        case CL_POWS:
+        default:
+            ev = (1u << P) - 1u;       // general x^y (dormant crossover flavours only): full semantics decide
+            break;
+        }
+    }
+}
+
+}  // namespace dev
+}  // namespace closyr

@@ -1,0 +1,229 @@
+/*
+ * closyr_b200.h -- C ABI of the B200-native scoring path for closyr (plain C, no exceptions, no torch types).
+ *
+ * Drop-in boundary.  The reference has no FFI; the boundary is the Clojure closure
+ *     (partial ops/score-fn run-args run-config)        src/closyr/symbolic_regression.clj:474-478
+ * stored as :score-fn (src/closyr/ga.clj:11-17) and called per phenotype (src/closyr/ga.clj:25-29), plus
+ * ops-eval/eval-vec-pheno used by the report (src/closyr/ops.clj:291-293).  The entry points below are
+ * what a Java FFM (Panama) / JNA binding of those two functions binds; INTEGRATION.md shows the binding.
+ * All file:line citations are relative to the reference checkout.
+ *
+ * Every function returns 0 on success or a negative CLOSYR_E_* code; closyr_last_error() gives the text.
+ * The library never keeps a caller pointer after a call returns.
+ */
+#ifndef CLOSYR_B200_H
+#define CLOSYR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLOSYR_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------
+ * Sentinels (src/closyr/ops.clj:24-36)
+ * ---------------------------------------------------------------------------------------------- */
+#define CLOSYR_MIN_SCORE (-100000000.0)
+#define CLOSYR_MAX_RESID (1000000.0)
+#define CLOSYR_DEFAULT_MAX_LEAFS 40
+
+/* ------------------------------------------------------------------------------------------------
+ * Bytecode ISA v1 (frozen; DESIGN.md "Bytecode").  One instruction = one uint32:
+ *     bits 0..7 opcode, bits 8..15 `a` (spill slot), bits 16..31 `b` (constant index or signed exponent).
+ * The machine is a postfix evaluator whose top of stack is the accumulator `acc`; the rest of the
+ * operand stack is addressed by STATIC slot numbers chosen by the compiler (the depth of a postfix
+ * program is known at every instruction), so the kernel keeps slots 0..3 in registers.
+ * Leaf operands (x, constants) are fused into the arithmetic instruction that consumes them.
+ * ---------------------------------------------------------------------------------------------- */
+enum closyr_opcode {
+    CL_END = 0,
+    CL_LDX = 1,      /* acc = x                                                        */
+    CL_LDC = 2,      /* acc = c[b]                                                     */
+    CL_LDZ = 3,      /* acc = c[b] + i*c[b+1]   (Complex literal; forces full semantics) */
+    CL_LDSPEC = 4,   /* acc = a==0 ? ComplexInfinity : Indeterminate                   */
+    CL_ADDX = 5,     /* acc = acc + x                                                  */
+    CL_ADDC = 6,     /* acc = acc + c[b]                                               */
+    CL_MULX = 7,     /* acc = acc * x                                                  */
+    CL_MULC = 8,     /* acc = acc * c[b]                                               */
+    CL_NEG = 9,      /* acc = -acc          (Times(-1, acc))                           */
+    CL_RECIP = 10,   /* acc = acc^-1        (1/0.0 -> ComplexInfinity)                 */
+    CL_SQR = 11,     /* acc = acc*acc       (Power(acc, 2))                            */
+    CL_SQRT = 12,    /* acc = acc^(1/2)                                                */
+    CL_RSQRT = 13,   /* acc = 1/(acc^(1/2)) (Power(acc, -1/2))                         */
+    CL_POWI = 14,    /* acc = acc^b, b = int16, 3 <= |b| <= 32 or b == -2: square-and-multiply, MSB first */
+    CL_POWC = 15,    /* acc = acc^c[b]      (real literal exponent, general pow)       */
+    CL_EXP = 16,     /* acc = E^acc                                                    */
+    CL_LOG = 17,
+    CL_SIN = 18,
+    CL_COS = 19,
+    CL_TAN = 20,
+    CL_ASIN = 21,
+    CL_ACOS = 22,
+    CL_ABS = 23,
+    CL_ST = 24,      /* slot[a] = acc                (generic form, any a < 64)        */
+    CL_ADDS = 25,    /* acc = slot[a] + acc                                            */
+    CL_MULS = 26,    /* acc = slot[a] * acc                                            */
+    CL_POWS = 27,    /* acc = slot[a] ^ acc          (general pow, any a)              */
+    CL_ST0 = 28,     /* CL_ST0 + a   : slot[a] = acc       for a in 0..3 (register slots) */
+    CL_ADDS0 = 32,   /* CL_ADDS0 + a : acc = slot[a] + acc for a in 0..3               */
+    CL_MULS0 = 36,   /* CL_MULS0 + a : acc = slot[a] * acc for a in 0..3               */
+    CL_NUM_OPCODES = 40
+};
+#define CLOSYR_REG_SLOTS 4
+#define CLOSYR_MAX_SLOTS 64
+#define CLOSYR_MAX_CODE_WORDS 2048   /* per expression, including END and padding */
+#define CLOSYR_MAX_CONSTS 1024       /* per expression */
+#define CLOSYR_INSN(op, a, b) ((uint32_t)(op) | ((uint32_t)(a) << 8) | ((uint32_t)((uint16_t)(b)) << 16))
+
+/* per-expression metadata word: bits 0..15 leafCount (saturating), 16..23 CL_F_* flags, 24..31 slots used */
+#define CL_F_CONST 0x01        /* expression does not depend on x (eval.clj:83-96 constant path)       */
+#define CL_F_UNSUPPORTED 0x02  /* exceeds a structural limit above; scored as min-score                */
+#define CL_F_NIL 0x04          /* whole expression is Indeterminate: eval returns nil (eval.clj:59-62) */
+#define CLOSYR_META(leafs, flags, nslots) \
+    ((uint32_t)((leafs) > 65535 ? 65535 : (leafs)) | ((uint32_t)(flags) << 16) | ((uint32_t)(nslots) << 24))
+
+/* result flags written per expression by closyr_score_batch */
+#define CL_R_TOO_BIG 0x01        /* leafs > max-leafs => min-score (ops.clj:128-129)                   */
+#define CL_R_MIN_SCORE 0x02      /* nil / throwing eval => min-score (ops.clj:131-136)                 */
+#define CL_R_FULL_SEMANTICS 0x04 /* at least one 128-point chunk left the IEEE-real fast path          */
+
+/*
+ * The population: one flat struct-of-arrays buffer (north star (1)).  Programs are concatenated;
+ * each program starts on a 16-byte boundary (code padded with CL_END to a multiple of 4 words,
+ * constants padded to a multiple of 2 doubles) so a program can be staged with one TMA bulk copy.
+ * For a constant expression whose head has `argc` arguments, aux = argc<<16 | offset (in doubles, inside
+ * this expression's pool) of an argc-entry table holding each argument's literal value or +Inf: the
+ * reference decodes such a result per argument when argc equals the point count (eval.clj:109).
+ */
+typedef struct closyr_population {
+    int64_t n_expr;
+    const uint32_t *code;       /* all instruction words                                   */
+    const uint32_t *code_off;   /* [n_expr + 1] word offsets into code, multiples of 4     */
+    const double *consts;       /* all constant pools                                      */
+    const uint32_t *const_off;  /* [n_expr + 1] offsets into consts, multiples of 2        */
+    const uint32_t *meta;       /* [n_expr] CLOSYR_META words                              */
+    const uint32_t *aux;        /* [n_expr] see above; 0 when unused                       */
+} closyr_population;
+
+/* ------------------------------------------------------------------------------------------------
+ * Error codes
+ * ---------------------------------------------------------------------------------------------- */
+#define CLOSYR_OK 0
+#define CLOSYR_E_ARG (-1)      /* bad argument                                 */
+#define CLOSYR_E_CUDA (-2)     /* CUDA runtime error, see closyr_last_error    */
+#define CLOSYR_E_NO_GPU (-3)   /* no usable CUDA device: there is NO CPU fallback */
+#define CLOSYR_E_STATE (-4)    /* call order (e.g. score before set_points)    */
+#define CLOSYR_E_PARSE (-5)    /* expression text could not be parsed          */
+#define CLOSYR_E_NOMEM (-6)
+
+typedef struct closyr_ctx closyr_ctx;
+typedef struct closyr_builder closyr_builder;
+
+const char *closyr_version(void);
+/* text of the last error on this thread (ctx may be NULL for creation / builder errors) */
+const char *closyr_last_error(const closyr_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Context: owns the CUDA streams, device buffers and pinned staging of 1..8 GPUs of one box.
+ * Replaces the per-run state the reference keeps in `run-args`
+ * (src/closyr/symbolic_regression.clj:355-383): xs/ys are marshalled once and stay resident.
+ * ---------------------------------------------------------------------------------------------- */
+#define CLOSYR_SHARD_POPULATION 0u /* expressions split across the devices, no collective (default)   */
+#define CLOSYR_SHARD_POINTS 1u     /* points split across devices; partial (sum,max) combined in a fixed tree */
+
+int closyr_ctx_create(const int *devices, int n_devices, uint32_t flags, closyr_ctx **out);
+void closyr_ctx_destroy(closyr_ctx *ctx);
+int closyr_ctx_device_count(const closyr_ctx *ctx);
+
+/* replaces doubles->exprs / exprs->exprs-list / :input-ys-vec (common.clj:30-35, 68-76); copies */
+int closyr_set_points(closyr_ctx *ctx, const double *xs, const double *ys, int64_t n);
+
+/*
+ * Batch form of ops/score-fn (src/closyr/ops.clj:119-136) for a whole generation: host buffers in,
+ * host buffers out (H2D of the population, kernels, D2H of scores inside the call).
+ * out_scores[n_expr] doubles; out_flags[n_expr] CL_R_* bytes (may be NULL).
+ */
+int closyr_score_batch(closyr_ctx *ctx, const closyr_population *pop, int32_t max_leafs, double *out_scores,
+                       uint8_t *out_flags);
+
+/* the same in three steps, so a caller (and bench.py) can keep a population resident in HBM */
+int closyr_upload_population(closyr_ctx *ctx, const closyr_population *pop);
+int closyr_score_resident(closyr_ctx *ctx, int32_t max_leafs, float *device_ms /* may be NULL */);
+int closyr_download_scores(closyr_ctx *ctx, double *out_scores, uint8_t *out_flags);
+
+/*
+ * Batch form of ops-eval/eval-vec-pheno (src/closyr/ops/eval.clj:99-112) on an explicit xs vector
+ * (the report path evaluates on xs and on the +-35 % extended domain, eval.clj:123-175).
+ * out_f is [n_expr * n] row-major; out_status[i]: 0 vector valid, 1 nil, 2 the reference would throw.
+ */
+int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const double *xs, int64_t n, double *out_f,
+                      uint8_t *out_status);
+
+/*
+ * ops/compute-score-from-actuals-and-expecteds (src/closyr/ops.clj:98-116) on caller-provided f(xs):
+ * residuals (ops.clj:78-90), their sum and max, and the score with the length deduction for `leafs`.
+ * out3 = { score, resid-sum, max-resid }.  The same device reduction and epilogue as closyr_score_batch.
+ */
+int closyr_score_from_values(closyr_ctx *ctx, const double *f_of_xs, const double *ys, int64_t n, int32_t leafs,
+                             double *out3);
+
+/*
+ * Device-side ranking of the scores of the resident population, bit-identical to the host's
+ * (reverse (sort-by :score pop)) including tie order (src/closyr/ops.clj:195-201): descending score,
+ * ties in DEscending original index.  Writes the first k indices.
+ */
+int closyr_rank_resident(closyr_ctx *ctx, int64_t k, int64_t *out_indices);
+
+/* point-sharded building blocks (used by one-process-per-GPU launchers, see closyr_b200/sharder.py):
+ * partials[3*n_expr] = {sum, max, nonreal_count} of this device's point range, combined afterwards. */
+int closyr_score_partials_resident(closyr_ctx *ctx, int32_t max_leafs, int64_t chunk_begin, int64_t chunk_end,
+                                   void *dev_partials /* device pointer, 3*n_expr doubles */);
+int closyr_finalize_partials(closyr_ctx *ctx, const void *dev_partials_all /* [n_parts][3*n_expr] */, int n_parts,
+                             int32_t max_leafs);
+
+/* measurement helpers used by bench.py (not part of the scoring semantics) */
+int closyr_l2_flush(closyr_ctx *ctx);
+int closyr_fp64_peak_probe(closyr_ctx *ctx, double *dfma_per_second); /* register-resident DFMA chain */
+int64_t closyr_kernel_launch_count(const closyr_ctx *ctx);
+
+/* pinned host memory for population buffers written directly by the caller (FFM MemorySegment) */
+void *closyr_host_alloc(size_t bytes);
+void closyr_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Expression compiler: lowers expression trees to the bytecode above (north star (1)).  In the Clojure
+ * integration the same lowering walks the IExpr directly (clj/closyr/gpu/compile.clj); this C entry
+ * point takes Symja text -- IExpr.fullFormString() or the printed form (str expr).
+ * ---------------------------------------------------------------------------------------------- */
+#define CLOSYR_BUILDER_PINNED 1u
+
+int closyr_builder_create(uint32_t flags, closyr_builder **out);
+void closyr_builder_destroy(closyr_builder *b);
+void closyr_builder_clear(closyr_builder *b);
+/* appends one expression; on CLOSYR_E_PARSE nothing is appended */
+int closyr_builder_add(closyr_builder *b, const char *expr_text);
+/* appends n expressions, compiling on nthreads host threads (0 = all cores); order is preserved */
+int closyr_builder_add_many(closyr_builder *b, const char *const *expr_texts, int64_t n, int nthreads);
+int closyr_builder_view(const closyr_builder *b, closyr_population *out);
+
+/* canonical Symja FullForm text of a parsed expression (malloc'd; free with closyr_free) */
+int closyr_to_fullform(const char *expr_text, char **out);
+int closyr_leaf_count(const char *expr_text, int32_t *out);
+void closyr_free(void *p);
+
+/*
+ * Synthetic populations for measurement: seeded random expression trees.
+ * mix 0 = "GA mix" (max-leafs 40 configs), 1 = "transcendental-heavy" (config 4).
+ * Appends n_expr programs to `b`; when out_texts != NULL it receives n_expr malloc'd FullForm strings
+ * (free each with closyr_free) so a checker can score the same population.
+ */
+int closyr_generate_population(closyr_builder *b, uint64_t seed, int64_t n_expr, int32_t max_leafs, int32_t mix,
+                               char **out_texts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOSYR_B200_H */

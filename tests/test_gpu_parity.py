@@ -1,0 +1,332 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(closyr_b200/libclosyr_b200.so) and is compared with the CPU oracle on the same seeded inputs.
+
+Tolerances: scores of transcendental expressions 1e-9 relative (BASELINE.json north star); everything that
+is integer, index or pure IEEE arithmetic (+, *, /, sqrt, integer powers, the reduction tree, the score
+epilogue, flags, ranking) is bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import closyr_b200 as cb
+from closyr_b200 import _lib as L
+from closyr_b200 import ops
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+INF = float("inf")
+REL_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cb.Context([0])
+    yield c
+    c.close()
+
+
+def synth_points(n):
+    """xs over the reference's example span, ys = the integration-test objective."""
+    xs = (np.pi / 15.0) * 49.0 * np.arange(n) / max(1, n - 1)
+    ys = 2.0 + 1.5 * xs / np.pi + np.cos(xs)
+    return xs, ys
+
+
+def gpu_scores(ctx, texts, xs, ys, max_leafs=40):
+    b = cb.PopulationBuilder()
+    b.add_many(texts)
+    ctx.set_points(xs, ys)
+    s, f = ctx.score_batch(b.view(), max_leafs)
+    b.close()
+    return s, f
+
+
+def assert_scores_close(got, want, texts=None):
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    i = int(np.argmax(err))
+    assert err[i] <= REL_TOL, "expr %d %s: gpu %r oracle %r" % (i, texts[i] if texts else "", got[i], want[i])
+
+
+# ------------------------------------------------------------------ the reference's own known-answer tests
+def run_args(ctx, xs, ys):
+    return ops.to_run_args(xs, ys, ctx=ctx)
+
+
+def test_score_fn_simple(ctx):  # test/closyr/ops_test.clj:18-28
+    ra = run_args(ctx, [0.5, 1.0, 2.0], [0, 1, 2])
+    assert ops.score_fn(ra, {"max-leafs": ops.default_max_leafs}, ops.to_phenotype("x*x-1/2")) == -3.0000147
+
+
+def test_score_fn_too_big(ctx):  # ops_test.clj:30-39
+    ra = run_args(ctx, [0.5, 1.0, 2.0], [0, 1, 2])
+    assert ops.score_fn(ra, {"max-leafs": 0}, ops.to_phenotype("x*x-1/2")) == ops.min_score
+
+
+def test_score_fn_failing_eval(ctx):  # ops_test.clj:41-65: nil / throwing eval => min-score
+    ra = run_args(ctx, [0.5, 1.0, 2.0], [0, 1, 2])
+    cfg = {"max-leafs": 40}
+    assert ops.score_fn(ra, cfg, {"expr": "Indeterminate"}) == ops.min_score      # eval returns nil
+    assert ops.score_fn(ra, cfg, {"expr": "Complex(0,1)"}) == ops.min_score       # toNumber throws
+    assert ops.score_fn(ra, cfg, {"expr": "Plus((("}) == ops.min_score            # any exception
+
+
+def test_compute_score_from_actuals_and_expecteds(ctx):  # ops_test.clj:68-76, 103-112
+    p = ops.to_phenotype("Sin(x)+1/2")
+    assert ops.compute_score_from_actuals_and_expecteds(p, [0.5], [1.0], 10, ctx) == -1.500015
+    assert ops.compute_score_from_actuals_and_expecteds(p, [0.5], [1.0], 0, ctx) == -1.5
+
+
+def test_compute_residuals(ctx):  # ops_test.clj:192-203
+    assert ops.compute_residual(10.0, 5.0, ctx) == 5.0
+    assert ops.compute_residual(INF, 5.0, ctx) == ops.max_resid
+    assert ops.compute_residual(INF, INF, ctx) == ops.max_resid
+    assert ops.compute_residual(1.0, float("nan"), ctx) == ops.max_resid
+
+
+def test_readme_initial_population(ctx):  # README.md:55 (config 1 data), all-x population
+    xs, ys = [0, 1, 2, 3, 4, 5, 6], [1, 2, 30, 4, 5, 6, 10]
+    ra = run_args(ctx, xs, ys)
+    scores, _ = ops.score_batch(ra, {"max-leafs": 40}, [ops.to_phenotype("x*1")] * 25)
+    assert scores.tolist() == [-38.57143242857143] * 25
+
+
+@pytest.mark.parametrize("expr,xs,want", [
+    ("x-1/2", [0.5, 1.0], [0.0, 0.5]),                       # ops_eval_test.clj:60-66
+    ("x*1", [0.5, 1.0], [0.5, 1.0]),                         # :82-88
+    ("x-1/2", [INF], [INF]),                                 # :161-166
+    ("x-Infinity", [0.0], [-INF]),                           # :168-173
+    ("E-1/2", [0.5], [2.218281828459045]),                   # :176-180
+    ("1-1/2", [0.5], [0.5]),                                 # :182-186
+    ("x-1/2", [0.5], [0.0]),                                 # :189-193
+    ("x*Sin(x)-1/2", [0.0, 0.5, 1.0], [-0.5, -0.2602872306978985, 0.3414709848078965]),   # :195-199
+    ("Sqrt(x-1)", [0.0, 0.5, 1.0], [INF, INF, 0.0]),         # :201-206 complex => +Inf
+    ("1", [0.0, 0.5, 1.0], [1.0, 1.0, 1.0]),                 # :208-212
+    ("Infinity", [0.0, 0.5, 1.0], [0.0, 0.5, 1.0]),          # :214-218 (->phenotype replaces it by x)
+    ("-1", [0.0, 0.5, 1.0], [-1.0, -1.0, -1.0]),             # :220-224
+    ("0.123", [0.0, 0.5, 1.0], [0.123, 0.123, 0.123]),       # :226-230
+    ("-1+1", [0.0, 0.5, 1.0], [0.0, 0.0, 0.0]),              # :232-236
+    ("x", [0.0, 0.5, 1.0], [0.0, 0.5, 1.0]),                 # :238-242
+    ("Indeterminate", [0.5], [0.5]),                         # :90-96 (->phenotype replaces it by x)
+])
+def test_eval_vec_pheno_known_answers(ctx, expr, xs, want):
+    ra = run_args(ctx, xs, [0.0] * len(xs))
+    got = ops.eval_vec_pheno(ops.to_phenotype(expr), ra)
+    if expr == "x*Sin(x)-1/2":
+        assert got[0] == want[0]
+        np.testing.assert_allclose(got, want, rtol=1e-15)
+    else:
+        assert got == want
+
+
+def test_eval_nil_and_throw(ctx):  # ops_eval_test.clj:98-112; eval.clj:83-96
+    ra = run_args(ctx, [0.5], [0.0])
+    assert ops.eval_vec_pheno({"expr": "Indeterminate"}, ra) is None
+    with pytest.raises(ArithmeticError):
+        ops.eval_vec_pheno({"expr": "Complex(0,1)"}, ra)
+
+
+@pytest.mark.parametrize("n", [20, 40, 80, 160, 320])
+def test_eval_benchmark_vectors_exact(ctx, n):  # ops_eval_test.clj:245-301
+    xs = np.arange(n, dtype=np.float64)
+    ra = run_args(ctx, xs, xs)
+    assert ops.eval_vec_pheno(ops.to_phenotype("x*x-1/2"), ra) == [x * x - 0.5 for x in xs.tolist()]
+
+
+def test_constant_ast_quirk(ctx):  # eval.clj:109
+    ra = run_args(ctx, [0.5, 1.0], [0.0, 0.0])
+    assert ops.eval_vec_pheno(ops.to_phenotype("E-1/2"), ra) == [-0.5, INF]
+    assert ops.score_fn(ra, {"max-leafs": 40}, ops.to_phenotype("E-1/2")) == O.score_fn("Plus(Rational(-1,2),E)", [0.5, 1.0], [0, 0], 40)
+
+
+# ------------------------------------------------------------------ seeded random populations vs the oracle
+@pytest.mark.parametrize("n_points", [7, 100, 128, 129, 1000, 4099])
+@pytest.mark.parametrize("mix,max_leafs", [(0, 40), (1, 80)])
+def test_random_population_matches_oracle(ctx, n_points, mix, max_leafs):
+    xs, ys = synth_points(n_points)
+    b = cb.PopulationBuilder()
+    texts = b.generate(888 + n_points, 400, max_leafs, mix, want_texts=True)
+    ctx.set_points(xs, ys)
+    got, flags = ctx.score_batch(b.view(), max_leafs)
+    want, _ = O.score_batch(texts, xs, ys, max_leafs)
+    assert_scores_close(got, want, texts)
+    assert int(np.argmax(got)) == int(np.argmax(want))          # identical best-expression selection
+    assert ((flags & L.R_MIN_SCORE) != 0).tolist() == (want == O.MIN_SCORE).tolist()
+    # device ranking == the host's (reverse (sort-by :score ...)) on the same scores, bit for bit
+    order = ctx.rank()
+    host = np.argsort(got, kind="stable")[::-1]
+    assert order.tolist() == host.tolist()
+
+
+def arithmetic_population(rng, count):
+    """Expressions that only use correctly rounded IEEE operations: the GPU must match bit for bit."""
+    leaves = ["x", "x", "x", "1/2", "1/10", "2", "10", "-1", "1.1", "0.9", "3/7"]
+
+    def gen(d):
+        if d == 0 or rng.random() < 0.25:
+            return leaves[rng.integers(len(leaves))]
+        k = rng.integers(7)
+        if k == 0:
+            return "Plus(%s,%s)" % (gen(d - 1), gen(d - 1))
+        if k == 1:
+            return "Times(%s,%s)" % (gen(d - 1), gen(d - 1))
+        if k == 2:
+            return "Plus(%s,%s,%s)" % (gen(d - 1), gen(d - 1), gen(d - 1))
+        if k == 3:
+            return "Power(%s,%d)" % (gen(d - 1), [2, -1, -2, 3, 5, -3][rng.integers(6)])
+        if k == 4:
+            return "Power(%s,Rational(%d,2))" % (gen(d - 1), [1, -1][rng.integers(2)])
+        if k == 5:
+            return "Times(%s,%s,%s)" % (gen(d - 1), gen(d - 1), gen(d - 1))
+        return "Abs(%s)" % gen(d - 1)
+
+    return [gen(5) for _ in range(count)]
+
+
+@pytest.mark.parametrize("n_points", [3, 127, 128, 1025, 5000])
+def test_arithmetic_population_is_bit_exact(ctx, n_points):
+    rng = np.random.default_rng(12345 + n_points)
+    texts = [cb.to_fullform(t) for t in arithmetic_population(rng, 300)]
+    xs = rng.uniform(-3.0, 8.0, n_points)
+    xs[0] = 0.0
+    ys = rng.uniform(-5.0, 5.0, n_points)
+    got, _ = gpu_scores(ctx, texts, xs, ys, 200)
+    want, _ = O.score_batch(texts, xs, ys, 200, sum_mode=O.SUM_CUDA_TREE)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, "expr %s gpu %r oracle %r" % (texts[bad[0]], got[bad[0]], want[bad[0]])
+
+
+def test_eval_batch_matches_oracle(ctx):
+    xs, _ = synth_points(300)
+    xs = np.concatenate([[-2.0, -0.5, 0.0], xs])
+    b = cb.PopulationBuilder()
+    texts = b.generate(4242, 200, 40, 0, want_texts=True)
+    f, status = ctx.eval_batch(b.view(), xs)
+    for i, t in enumerate(texts):
+        try:
+            want = O.eval_vec_pheno(t, xs)
+        except ArithmeticError:
+            assert status[i] == 2
+            continue
+        if want is None:
+            assert status[i] == 1
+            continue
+        assert status[i] == 0
+        got = f[i]
+        assert (np.isinf(got) == np.isinf(want)).all(), t
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-9, atol=1e-300, err_msg=t)
+
+
+SEMANTIC_CASES = [
+    # poles: 1/0.0 is ComplexInfinity
+    "Power(x,-1)", "Plus(1,Power(x,-1))", "Power(Plus(1,Power(x,-1)),-1)", "Times(x,Power(x,-1))",
+    "Power(E,Times(-1,Power(x,-2)))", "Plus(Power(x,-1),Times(-1,Power(x,-1)))", "Sin(Power(x,-1))",
+    "Log(x)", "Power(E,Log(x))", "Power(E,Times(2,Log(x)))", "Log(Power(x,-1))", "Abs(Power(x,-1))",
+    # complex excursions that come back to the real line (A9)
+    "Cos(Power(x,Rational(1,2)))", "Power(Power(Plus(-1,x),Rational(1,2)),2)",
+    "Times(Power(Plus(-1,x),Rational(1,2)),Power(Plus(-2,x),Rational(1,2)))",
+    "Times(Power(Plus(-1,x),Rational(1,2)),Power(Plus(-2,x),Rational(-1,2)))",
+    "Abs(Power(x,Rational(1,2)))", "Abs(Log(x))", "Power(Log(x),2)", "Cos(ArcCos(x))", "Sin(ArcSin(x))",
+    "Abs(ArcSin(x))", "Abs(ArcCos(x))", "Power(x,Rational(3,2))", "Power(x,0.5)", "Power(x,1.5)", "Power(x,-2.5)",
+    "Tan(Power(x,Rational(1,2)))", "Power(E,Power(x,Rational(1,2)))", "Log(Log(x))", "Power(Log(x),-1)",
+    "Power(Plus(-1,x),Rational(-1,2))", "ArcSin(Times(2,x))", "ArcCos(Times(2,x))", "Power(ArcSin(x),2)",
+    "Times(Power(x,Rational(1,2)),Power(x,Rational(1,2)))", "Power(Sin(x),Rational(1,2))", "Power(x,x)",
+    "Power(2,x)", "Power(-2,x)", "Power(x,Sin(x))", "Power(Cos(x),x)", "Power(Sin(x),Cos(x))",
+    # literals that are not real numbers
+    "Plus(x,Complex(0,1))", "Times(x,Complex(0,1))", "Power(Times(x,Complex(0,1)),2)", "Plus(x,DirectedInfinity())",
+    "Times(x,DirectedInfinity())", "Plus(x,Indeterminate)", "Plus(x,DirectedInfinity(1))", "Times(x,DirectedInfinity(-1))",
+    "Power(E,Times(x,DirectedInfinity(-1)))", "unknownfn(x)", "Plus(x,y)",
+    # constants
+    "Plus(Rational(-1,2),E)", "Sin(Rational(1,2))", "Power(-2,Rational(1,2))", "Log(-1)", "Power(0,-1)", "Pi",
+    "DirectedInfinity(1)", "DirectedInfinity()", "Indeterminate", "Power(2,Rational(1,2))",
+    # overflow / big exponents
+    "Power(E,Power(E,Power(E,x)))", "Power(x,40)", "Power(x,-40)", "Power(Times(1000000,x),32)", "Power(x,100)",
+]
+
+
+def test_semantic_cases_match_oracle(ctx):
+    xs = np.array([-3.0, -1.5, -1.0, -0.5, -0.0, 0.0, 0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 7.5, 100.0, 1e6, 1e300])
+    ys = np.linspace(-1.0, 2.0, len(xs))
+    got, flags = gpu_scores(ctx, SEMANTIC_CASES, xs, ys, 40)
+    want, _ = O.score_batch(SEMANTIC_CASES, xs, ys, 40)
+    assert_scores_close(got, want, SEMANTIC_CASES)
+    ctx.set_points(xs, ys)
+    b = cb.PopulationBuilder()
+    b.add_many(SEMANTIC_CASES)
+    f, status = ctx.eval_batch(b.view(), xs)
+    for i, t in enumerate(SEMANTIC_CASES):
+        try:
+            w = O.eval_vec_pheno(t, xs)
+        except ArithmeticError:
+            assert status[i] == 2, t
+            continue
+        if w is None:
+            assert status[i] == 1, t
+            continue
+        assert status[i] == 0, t
+        assert (np.isinf(f[i]) == np.isinf(w)).tolist() == [True] * len(xs), "%s gpu %r oracle %r" % (t, f[i], w)
+        fin = np.isfinite(w)
+        np.testing.assert_allclose(f[i][fin], w[fin], rtol=1e-9, atol=1e-300, err_msg=t)
+
+
+def test_scores_are_identical_for_every_tiling(ctx):
+    """The reduction tree is fixed: a small population (many tiles per expression, partials + finalize kernel)
+    and the same expressions inside a large population (one tile per expression) give bit-identical scores."""
+    n = 70000
+    xs, ys = synth_points(n)
+    b = cb.PopulationBuilder()
+    texts = b.generate(99, 24, 40, 0, want_texts=True)
+    ctx.set_points(xs, ys)
+    small, _ = ctx.score_batch(b.view(), 40)
+    big = cb.PopulationBuilder()
+    big.add_many(texts)
+    big.generate(100, 20000, 10, 0)
+    large, _ = ctx.score_batch(big.view(), 40)
+    assert small.tolist() == large[:24].tolist()
+    want, _ = O.score_batch(texts, xs, ys, 40)
+    assert_scores_close(small, want, texts)
+
+
+def test_resident_api_and_launch_count(ctx):
+    xs, ys = synth_points(512)
+    b = cb.PopulationBuilder()
+    b.generate(5, 3000, 40, 0)
+    ctx.set_points(xs, ys)
+    before = ctx.kernel_launches
+    ctx.upload_population(b.view())
+    ms = ctx.score_resident(40)
+    s1, f1 = ctx.download_scores()
+    s2, f2 = ctx.score_batch(b.view(), 40)
+    assert ms > 0.0
+    assert ctx.kernel_launches > before
+    assert s1.tolist() == s2.tolist() and f1.tolist() == f2.tolist()
+
+
+def test_empty_inputs(ctx):
+    b = cb.PopulationBuilder()
+    ctx.set_points([1.0, 2.0], [1.0, 2.0])
+    s, f = ctx.score_batch(b.view(), 40)
+    assert len(s) == 0
+    b.add("x")
+    ctx.set_points([], [])
+    s, f = ctx.score_batch(b.view(), 40)
+    assert s.tolist() == [ops.min_score]          # (reduce max []) throws in the reference => min-score
+
+
+def test_duplicates_score_bit_equal_at_baseline_size(ctx):
+    """Config 3 shape (pop 100K x 4096 points): equal expressions get bit-equal scores wherever they sit, every
+    score is a finite number <= 0, and the device ranking is sorted."""
+    xs, ys = synth_points(4096)
+    b = cb.PopulationBuilder()
+    b.generate(888, 50000, 40, 0)
+    b.generate(888, 50000, 40, 0)                 # the same 50K again
+    ctx.set_points(xs, ys)
+    s, f = ctx.score_batch(b.view(), 40)
+    assert s[:50000].tolist() == s[50000:].tolist()
+    assert np.isfinite(s).all() and (s <= 0).all()
+    order = ctx.rank(1000)
+    assert (np.diff(s[order]) <= 0).all()
+    assert s[order[0]] == s.max()
