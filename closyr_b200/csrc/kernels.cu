@@ -99,6 +99,11 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
     uint32_t ev = run_real<4>(st.scode, st.sconst, x, v);
     if (is_const) ev = 0xfu;
     ev &= valid;
+    // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
+    nr &= valid;
     if (!__any_sync(FULL, ev != 0)) return false;
 #pragma unroll
     for (int j = 0; j < 4; j++) {

@@ -24,9 +24,9 @@ namespace dev {
 // real line helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool nonfinite(double x) { return (__double2hiint(x) & 0x7ff00000) == 0x7ff00000; }
-__device__ __forceinline__ bool is_neg_inf(double x)
+__device__ __forceinline__ bool is_inf(double x)
 {
-    return __double2hiint(x) == (int)0xfff00000 && __double2loint(x) == 0;
+    return ((unsigned)__double2hiint(x) << 1) == 0xffe00000u && __double2loint(x) == 0;
 }
 __device__ __forceinline__ bool is_integer_value(double y) { return !nonfinite(y) && floor(y) == y; }
 
@@ -59,8 +59,12 @@ __device__ __forceinline__ int ztag(Z v)
 __device__ __forceinline__ Z zv(double re, double im) { Z z; z.re = re; z.im = im; return z; }
 __device__ __forceinline__ Z zindet() { return zv(__longlong_as_double(0x7ff8000000000000ll), 0.0); }
 __device__ __forceinline__ Z zcinf() { return zv(__longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0x7ff0000000000000ll)); }
+// rounding noise must not decide whether a value is real, nor the side of a branch cut (DESIGN.md "Semantics")
+#define CLOSYR_CHOP_REL 1e-10
 __device__ __forceinline__ Z zmk(double re, double im)
 {
+    if (im != 0.0 && fabs(im) <= CLOSYR_CHOP_REL * fabs(re)) im = 0.0;
+    else if (re != 0.0 && fabs(re) <= CLOSYR_CHOP_REL * fabs(im)) re = 0.0;
     Z v = zv(re, im);
     int t = ztag(v);
     if (t == T_INDET) return zindet();
@@ -207,6 +211,9 @@ __device__ __noinline__ Z zasin(Z a)
     if (t == T_REAL) {
         if (fabs(a.re) <= 1.0) return zv(asin(a.re), 0.0);
         if (isinf(a.re)) return zcinf();
+        // real |x| > 1: same principal value, without the cancellation of the general formula
+        const double ax = fabs(a.re), l = log(ax + sqrt((ax - 1.0) * (ax + 1.0)));
+        return a.re > 0.0 ? zmk(3.141592653589793 / 2.0, -l) : zmk(-(3.141592653589793 / 2.0), l);
     }
     Z w = zlog(zadd(zsqrt1z(a), zmul_i(a)));
     int tw = ztag(w);
@@ -223,6 +230,8 @@ __device__ __noinline__ Z zacos(Z a)
     if (t == T_REAL) {
         if (fabs(a.re) <= 1.0) return zv(acos(a.re), 0.0);
         if (isinf(a.re)) return zcinf();
+        const double ax = fabs(a.re), l = log(ax + sqrt((ax - 1.0) * (ax + 1.0)));
+        return a.re > 0.0 ? zmk(0.0, l) : zmk(3.141592653589793, -l);
     }
     Z s = zsqrt1z(a);
     int ts = ztag(s);
@@ -356,9 +365,24 @@ __device__ __noinline__ Z full_eval(const uint32_t *__restrict__ scode, const do
 
 // ------------------------------------------------------------------------------------------------
 // fast path: P points per lane, IEEE real arithmetic, register-resident accumulator and slots 0..3.
-// Returns a bit mask (bit j = point j) of points that must be re-evaluated by full_eval.
+//
+// Invariant kept per point (v = the IEEE value here, s = the value of the full algebra):
+//   v finite  <=>  s is a finite real and v == s;   v = +-Inf  =>  s is ComplexInfinity or a directed infinity
+//   (IEEE cannot tell which);   v NaN, no event  =>  s is Indeterminate (absorbing: the point is not real).
+// The returned mask has bit j set when point j must be re-evaluated by full_eval because the invariant
+// cannot be kept:  (1) a function left its real domain (NaN out of a non-NaN input: the full algebra
+// continues over the complex numbers or with ComplexInfinity);  (2) an infinity reaches an instruction that
+// can turn it into a finite number (1/Inf = 0, E^-Inf = 0, Inf^-y = 0) -- whether that is right depends on
+// which infinity it was;  (3) literals that are not real, and general x^y.
 // ------------------------------------------------------------------------------------------------
 #define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
+#define CLOSYR_DOMAIN_OP(expr)                                                 \
+    CLOSYR_FORJ {                                                              \
+        const double in_ = acc[j];                                             \
+        const double r_ = (expr);                                              \
+        if (r_ != r_ && in_ == in_) ev |= 1u << j;                             \
+        acc[j] = r_;                                                           \
+    }
 
 template <int P>
 __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
@@ -375,10 +399,7 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
         const int b = (int)(w >> 16);
         w = scode[++pc];                                     // prefetch (the buffer has one word of slack)
         switch (op) {
-        case CL_END: {
-            CLOSYR_FORJ if (acc[j] != acc[j]) ev |= 1u << j;
-            return ev;
-        }
+        case CL_END: return ev;
         case CL_LDX: CLOSYR_FORJ acc[j] = x[j]; break;
         case CL_LDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = c; break; }
         case CL_LDZ:
@@ -388,26 +409,30 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
         case CL_MULX: CLOSYR_FORJ acc[j] = acc[j] * x[j]; break;
         case CL_MULC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] * c; break; }
         case CL_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;
-        case CL_RECIP: CLOSYR_FORJ acc[j] = 1.0 / acc[j]; break;
+        case CL_RECIP: CLOSYR_FORJ { if (is_inf(acc[j])) ev |= 1u << j; acc[j] = 1.0 / acc[j]; } break;
         case CL_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
-        case CL_SQRT: CLOSYR_FORJ acc[j] = sqrt(acc[j]); break;
-        case CL_RSQRT: CLOSYR_FORJ acc[j] = 1.0 / sqrt(acc[j]); break;
-        case CL_POWI: { const int n = (int)(short)b; CLOSYR_FORJ acc[j] = powi_real(acc[j], n); break; }
+        case CL_SQRT: CLOSYR_DOMAIN_OP(sqrt(in_)) break;
+        case CL_RSQRT: CLOSYR_DOMAIN_OP(is_inf(in_) ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / sqrt(in_)) break;
+        case CL_POWI: {
+            const int n = (int)(short)b;
+            CLOSYR_FORJ { if (n < 0 && is_inf(acc[j])) ev |= 1u << j; acc[j] = powi_real(acc[j], n); }
+            break;
+        }
         case CL_POWC: {
             const double y = sconst[b];
             if (nonfinite(y) || y == 0.0) { ev = (1u << P) - 1u; break; }
-            CLOSYR_FORJ acc[j] = pow(acc[j], y);
+            CLOSYR_DOMAIN_OP(is_inf(in_) ? __longlong_as_double(0x7ff8000000000000ll) : pow(in_, y))
             break;
         }
         case CL_EXP:
-            CLOSYR_FORJ { if (is_neg_inf(acc[j])) ev |= 1u << j; acc[j] = exp(acc[j]); }
+            CLOSYR_FORJ { if (is_inf(acc[j])) ev |= 1u << j; acc[j] = exp(acc[j]); }
             break;
-        case CL_LOG: CLOSYR_FORJ acc[j] = log(acc[j]); break;
+        case CL_LOG: CLOSYR_DOMAIN_OP(log(in_)) break;
         case CL_SIN: CLOSYR_FORJ acc[j] = sin(acc[j]); break;
         case CL_COS: CLOSYR_FORJ acc[j] = cos(acc[j]); break;
         case CL_TAN: CLOSYR_FORJ acc[j] = tan(acc[j]); break;
-        case CL_ASIN: CLOSYR_FORJ acc[j] = asin(acc[j]); break;
-        case CL_ACOS: CLOSYR_FORJ acc[j] = acos(acc[j]); break;
+        case CL_ASIN: CLOSYR_DOMAIN_OP(asin(in_)) break;
+        case CL_ACOS: CLOSYR_DOMAIN_OP(acos(in_)) break;
         case CL_ABS: CLOSYR_FORJ acc[j] = fabs(acc[j]); break;
         case CL_ST0 + 0: CLOSYR_FORJ s0[j] = acc[j]; break;
         case CL_ST0 + 1: CLOSYR_FORJ s1[j] = acc[j]; break;

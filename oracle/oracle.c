@@ -44,6 +44,36 @@
 #define MIN_SCORE (-100000000.0)
 #define MAX_RESID (1000000.0)
 
+/* ------------------------------------------------------------------ libm jitter (conditioning probe)
+ * Java's Math.*, glibc and CUDA's libdevice are all "within an ulp or two", not bit-identical.  To tell a
+ * real mismatch from an expression whose value is not determined by such libraries (e.g. Cos(E^(x^2)) at
+ * large x), tests evaluate the oracle again with every transcendental result nudged by one ulp up / down and
+ * only hold the 1e-9 bar where the oracle agrees with itself.  0 = off (default). */
+static int g_jitter = 0;                      /* 0 off; otherwise the seed of a random +-1 ulp pattern */
+static _Thread_local uint64_t t_jcnt = 0;     /* position in the pattern; reset per expression */
+void oracle_set_jitter(int seed) { g_jitter = seed; }
+static double J(double r)
+{
+    if (g_jitter == 0 || !isfinite(r)) return r;
+    uint64_t z = (t_jcnt += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return nextafter(r, (z & 1) ? INFINITY : -INFINITY);
+}
+#define exp(x) J(exp(x))
+#define log(x) J(log(x))
+#define sin(x) J(sin(x))
+#define cos(x) J(cos(x))
+#define tan(x) J(tan(x))
+#define sinh(x) J(sinh(x))
+#define cosh(x) J(cosh(x))
+#define asin(x) J(asin(x))
+#define acos(x) J(acos(x))
+#define atan2(y, x) J(atan2(y, x))
+#define hypot(x, y) J(hypot(x, y))
+#define pow(x, y) J(pow(x, y))
+
 /* ------------------------------------------------------------------ values */
 typedef struct { double re, im; } val_t;
 enum { T_REAL = 0, T_CPLX = 1, T_CINF = 2, T_INDET = 3 };
@@ -59,8 +89,14 @@ static val_t V(double re, double im) { val_t v = { re, im }; return v; }
 static val_t INDET(void) { return V(NAN, 0.0); }
 static val_t CINF(void) { return V(INFINITY, INFINITY); }
 /* normalise: one encoding per class */
+/* A complex result whose imaginary (real) part is rounding noise next to the other part is snapped onto
+ * the real (imaginary) axis: noise must not decide whether an element "is a real number" (eval.clj:74),
+ * nor which side of a branch cut it sits on.  PARITY UNPINNED (Symja's own chop rule is not observable here). */
+#define CHOP_REL 1e-10
 static val_t mk(double re, double im)
 {
+    if (im != 0.0 && fabs(im) <= CHOP_REL * fabs(re)) im = 0.0;
+    else if (re != 0.0 && fabs(re) <= CHOP_REL * fabs(im)) re = 0.0;
     val_t v = { re, im };
     switch (tag(v)) {
     case T_INDET: return INDET();
@@ -211,6 +247,9 @@ static val_t v_asin(val_t a)
     if (t == T_REAL) {
         if (fabs(a.re) <= 1.0) return V(asin(a.re), 0.0);
         if (isinf(a.re)) return CINF();
+        /* real |x| > 1: the same principal value, written without the cancellation of the general formula */
+        double ax = fabs(a.re), l = log(ax + sqrt((ax - 1.0) * (ax + 1.0)));
+        return a.re > 0.0 ? mk(M_PI / 2.0, -l) : mk(-(M_PI / 2.0), l);
     }
     val_t w = v_log(v_add(v_sqrt1z(a), v_mul_i(a)));
     int tw = tag(w);
@@ -227,6 +266,8 @@ static val_t v_acos(val_t a)
     if (t == T_REAL) {
         if (fabs(a.re) <= 1.0) return V(acos(a.re), 0.0);
         if (isinf(a.re)) return CINF();
+        double ax = fabs(a.re), l = log(ax + sqrt((ax - 1.0) * (ax + 1.0)));
+        return a.re > 0.0 ? mk(0.0, l) : mk(M_PI, -l);
     }
     val_t s = v_sqrt1z(a);
     int ts = tag(s);
@@ -646,6 +687,7 @@ int oracle_leaf_count(const char *expr)
 /* eval-vec-pheno; see eval_vec for the status codes */
 int oracle_eval(const char *expr, const double *xs, int64_t n, double *out)
 {
+    t_jcnt = (uint64_t)g_jitter * 0xD1B54A32D192ED03ull + strlen(expr);
     node *e = parse(expr);
     if (!e) return 3;
     int st = eval_vec(e, xs, n, out);
@@ -679,6 +721,7 @@ double oracle_score_from_f(const double *f, const double *ys, int64_t n, int lea
 static double score_one(const char *expr, const double *xs, const double *ys, int64_t n, int max_leafs,
                         int sum_mode, double *f, double *scratch)
 {
+    t_jcnt = (uint64_t)g_jitter * 0xD1B54A32D192ED03ull + strlen(expr);
     node *e = parse(expr);
     if (!e) return MIN_SCORE;                       /* any exception => min-score (ops.clj:134-136) */
     double s;

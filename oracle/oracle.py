@@ -51,6 +51,8 @@ def lib():
                                          C.c_int, dp]
         L.oracle_score_batch.restype = C.c_int
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_jitter.argtypes = [C.c_int]
+        L.oracle_set_jitter.restype = None
         _lib = L
     return _lib
 
@@ -124,3 +126,78 @@ def score_batch(exprs, xs, ys, max_leafs=40, sum_mode=SUM_LEFT_FOLD, nthreads=0)
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def score_batch_conditioned(exprs, xs, ys, max_leafs=40, sum_mode=SUM_LEFT_FOLD, tol=1e-10, probes=8):
+    """Scores plus a mask of the expressions whose score is determined by fp64 arithmetic: the oracle is run
+    again `probes` times with every transcendental result moved by a random +-1 ulp (other, equally valid
+    math libraries); where its own scores move by more than `tol` relative, no implementation can be held
+    to 1e-9 (chaotic expressions such as Cos(E^(x^2)), exact cancellations that decide a branch)."""
+    base, _ = score_batch(exprs, xs, ys, max_leafs, sum_mode)
+    ok = np.ones(len(base), dtype=bool)
+    try:
+        for seed in range(1, probes + 1):
+            lib().oracle_set_jitter(seed)
+            other, _ = score_batch(exprs, xs, ys, max_leafs, sum_mode)
+            ok &= np.abs(other - base) <= tol * np.maximum(1.0, np.abs(base))
+    finally:
+        lib().oracle_set_jitter(0)
+    return base, ok
+
+
+def eval_conditioned(expr, xs, tol=1e-10, probes=16):
+    """eval_vec_pheno plus a per-point mask of the values the oracle reproduces under libm jitter."""
+    base = eval_vec_pheno(expr, xs)
+    if base is None:
+        return None, None
+    ok = np.ones(len(base), dtype=bool)
+    try:
+        for seed in range(1, probes + 1):
+            lib().oracle_set_jitter(seed)
+            other = eval_vec_pheno(expr, xs)
+            with np.errstate(invalid="ignore"):
+                same = (other == base) | (np.abs(other - base) <= tol * np.abs(base))
+            ok &= same
+    finally:
+        lib().oracle_set_jitter(0)
+    return base, ok
+
+
+def score_discrepancy_explained(expr, xs, ys, max_leafs, got, want, sum_mode=SUM_LEFT_FOLD, max_probes=256):
+    """True when the oracle itself moves by at least half of |got - want| under some +-1 ulp perturbation of
+    its math library: the expression sits on a knife edge (domain boundary, branch cut, chaotic argument)
+    where two correct implementations legitimately differ.  A systematic error of the implementation under
+    test is not reproducible this way, so it still fails."""
+    need = 0.5 * abs(got - want)
+    try:
+        for seed in range(1, max_probes + 1):
+            lib().oracle_set_jitter(seed)
+            if abs(score_fn(expr, xs, ys, max_leafs, sum_mode) - want) >= need:
+                return True
+    finally:
+        lib().oracle_set_jitter(0)
+    return False
+
+
+def eval_discrepancy_explained(expr, xs, got, want, max_probes=256):
+    """Per-point version of score_discrepancy_explained for eval vectors (inf = not a real number)."""
+    got = np.asarray(got, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        bad = ~((got == want) | (np.abs(got - want) <= 1e-9 * np.abs(want)))
+    todo = set(np.nonzero(bad)[0].tolist())
+    try:
+        for seed in range(1, max_probes + 1):
+            if not todo:
+                break
+            lib().oracle_set_jitter(seed)
+            other = eval_vec_pheno(expr, xs)
+            for k in list(todo):
+                if np.isinf(got[k]) != np.isinf(want[k]):
+                    hit = np.isinf(other[k]) == np.isinf(got[k])
+                else:
+                    hit = np.isinf(other[k]) != np.isinf(want[k]) or abs(other[k] - want[k]) >= 0.5 * abs(got[k] - want[k])
+                if hit:
+                    todo.discard(k)
+    finally:
+        lib().oracle_set_jitter(0)
+    return not todo, int(bad.sum())
