@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- measures the scoring hot path on B200 (contract in the task statement).
+
+A step = scoring ONE generation (every expression of the population against every point).
+Default workload = BASELINE.json configs[2] ("population 100K, max-leafs 40, 4096 points, population-sharded
+at 1/2/4/8 B200"), the configuration the metric "expr-point evals/sec and ms/generation at 1/2/4/8 B200" is
+quoted on; the population is split across ranks (strong scaling of a fixed generation).
+
+    python bench.py --gpus N --steps K --warmup W                 # this framework
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU restatement on the host cores
+
+Prints one JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (population, points, max_leafs, mix, description)
+    "c2": (1000, 1024, 40, 0, "configs[1]: pop 1000 x 1024 points, max-leafs 40"),
+    "c3": (100000, 4096, 40, 0, "configs[2]: pop 100K x 4096 points, max-leafs 40, GA mix"),
+    "c4": (1000000, 65536, 80, 1, "configs[3]: pop 1M x 65536 points, max-leafs 80, transcendental-heavy"),
+}
+SEED = 888   # echoes the reference's PRNG seed (src/closyr/util/prng.clj:59)
+
+# FP64-pipe instructions on the fast path of CUDA 12.9 libdevice's own routine for each operation, read from
+# sm_100a SASS (profiles/r01_libdevice_fp64_weights.md).  FROZEN: this table defines the algorithmic work of
+# an (expression, point) pair; it does not change when the kernels do.
+W_EPILOGUE = 4            # y - f, min with max-resid, sum, max
+OP_WEIGHT = {
+    5: 1, 6: 1, 7: 1, 8: 1,        # ADDX ADDC MULX MULC
+    10: 5, 11: 1, 12: 8, 13: 13,   # RECIP SQR SQRT RSQRT
+    15: 90, 16: 15, 17: 29,        # POWC EXP LOG
+    18: 17, 19: 17, 20: 28,        # SIN COS TAN
+    21: 23, 22: 24,                # ASIN ACOS
+    25: 1, 26: 1, 27: 90,          # ADDS MULS POWS
+    32: 1, 33: 1, 34: 1, 35: 1, 36: 1, 37: 1, 38: 1, 39: 1,   # ADDS0..3 MULS0..3
+}
+
+
+def synth_points(n):
+    """the reference's example span; ys = the integration-test objective."""
+    xs = (np.pi / 15.0) * 49.0 * np.arange(n, dtype=np.float64) / max(1, n - 1)
+    ys = 2.0 + 1.5 * xs / np.pi + np.cos(xs)
+    return xs, ys
+
+
+def algorithmic_work(arrays):
+    """Per expression: (weighted FP64 slots per point, instructions per point)."""
+    code = arrays["code"].astype(np.int64)
+    op = code & 0xFF
+    w = np.zeros(256, dtype=np.int64)
+    for k, v in OP_WEIGHT.items():
+        w[k] = v
+    slots = w[op]
+    powi = op == 14
+    if powi.any():
+        n = ((code[powi] >> 16) & 0xFFFF).astype(np.int64)
+        n = np.where(n >= 32768, n - 65536, n)
+        a = np.abs(n)
+        bits = np.floor(np.log2(np.maximum(a, 1))).astype(np.int64)
+        pop = np.array([bin(int(v)).count("1") for v in a], dtype=np.int64)
+        slots[powi] = bits + pop - 1 + np.where(n < 0, 5, 0)
+    insn = (op != 0).astype(np.int64)
+    off = arrays["code_off"].astype(np.int64)
+    starts = off[:-1]
+    per_slots = np.add.reduceat(slots, starts) if len(starts) else np.zeros(0, np.int64)
+    per_insn = np.add.reduceat(insn, starts) if len(starts) else np.zeros(0, np.int64)
+    return per_slots + W_EPILOGUE, per_insn
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of closyr's scoring path (oracle/oracle.c) on every host core.
+    The real reference (Clojure + Symja on a JVM) cannot run in this image: no JVM, no jars, no network."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    import closyr_b200 as cb
+
+    pop_n, n_points, max_leafs, mix, desc = WORKLOADS[args.workload]
+    sample = min(pop_n, args.cpu_sample)
+    xs, ys = synth_points(n_points)
+    b = cb.PopulationBuilder()
+    texts = b.generate(SEED, sample, max_leafs, mix, want_texts=True)
+    cores = O.max_threads()
+    for _ in range(args.warmup):
+        O.score_batch(texts[: max(1, sample // 10)], xs, ys, max_leafs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.score_batch(texts, xs, ys, max_leafs)
+    dt = time.perf_counter() - t0
+    value = sample * n_points * args.steps / dt
+    sample_desc = "first %d of %d expressions x all %d points per step" % (sample, pop_n, n_points)
+    line = {
+        "impl": "reference", "metric": "expr-point evals/sec", "value": value, "unit": "expr-points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps * (pop_n / sample),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "population": pop_n, "points": n_points, "max_leafs": max_leafs,
+                   "note": "CPU restatement of closyr's scorer (C, tree walk over complex values), not Symja/JVM; "
+                           "ms_per_step is extrapolated linearly from the sample to the full generation"},
+        "cpu_baseline": {"value": value, "unit": "expr-points/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "expr-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="closyr_b200", choices=["closyr_b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="population", choices=["population", "points"])
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="expressions scored by the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import closyr_b200 as cb
+    from closyr_b200 import sharder
+
+    rank, world, local = dist_env()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pop_n, n_points, max_leafs, mix, desc = WORKLOADS[args.workload]
+    xs, ys = synth_points(n_points)
+    builder = cb.PopulationBuilder(pinned=True)
+    builder.generate(SEED, pop_n, max_leafs, mix)
+    full = builder.view()
+    arrays = builder.arrays()
+    slots, insn = algorithmic_work(arrays)
+
+    by_points = args.shard == "points"
+    cuts = [0, pop_n] if by_points else sharder.plan_population_shards(arrays["code_off"], world)
+    lo, hi = (0, pop_n) if by_points else (cuts[rank], cuts[rank + 1])
+    mine = sharder.shard_view(full, lo, hi)
+    h2d = int(4 * (arrays["code_off"][hi] - arrays["code_off"][lo]) + 8 * (arrays["const_off"][hi] - arrays["const_off"][lo])
+              + (hi - lo) * 16 + 8)
+    d2h = int((hi - lo) * 9)
+
+    ctx = cb.Context([local])
+    ctx.set_points(xs, ys)
+    peak_dfma = ctx.fp64_peak_probe()          # register-resident DFMA chains on this GPU, this run
+
+    def step_resident():
+        if by_points:
+            t0 = time.perf_counter()
+            sharder.score_point_sharded(ctx, max_leafs, n_points, rank, world, dist, dev)
+            return 1e3 * (time.perf_counter() - t0)
+        return ctx.score_resident(max_leafs)
+
+    # ---- device-resident throughput ("value"): inputs already in HBM, CUDA events on the launching stream
+    ctx.upload_population(mine)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler.start()
+    dev_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.l2_flush()                          # L2 flushed between timed iterations (not inside the event pair)
+        dev_ms += step_resident()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    ms_per_step = max_over_ranks(dev_ms / args.steps)
+    value = pop_n * n_points / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: H2D of the generation + kernels + D2H of the scores
+    scores = None
+    for _ in range(max(1, args.warmup // 2)):
+        scores, flags = ctx.score_batch(mine, max_leafs) if not by_points else (None, None)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if by_points:
+            ctx.upload_population(mine)
+            scores, flags = sharder.score_point_sharded(ctx, max_leafs, n_points, rank, world, dist, dev)
+        else:
+            scores, flags = ctx.score_batch(mine, max_leafs)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e_value = pop_n * n_points / e2e_s
+
+    # ---- roofline of the dominant kernel (score_kernel): weighted FP64 slots / device time vs measured DFMA rate
+    my_slots = float(slots[lo:hi].sum()) * n_points
+    my_insn = float(insn[lo:hi].sum()) * n_points
+    if by_points:
+        my_slots /= world
+        my_insn /= world
+    achieved = my_slots / (dev_ms / args.steps * 1e-3)         # this rank's FP64 slots per second
+    roof = {
+        "bound": "fp64", "achieved": 2 * achieved / 1e12, "peak": 2 * peak_dfma / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / peak_dfma, "traffic": None,
+        "note": "non-tensor FP64 pipe: achieved = frozen libdevice-weighted FP64 instruction slots of the bytecode "
+                "x points / score_kernel time (CUDA events), x2 flop; peak = register-resident DFMA chain measured "
+                "in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry); theoretical 148 SM x 64 DFMA/clk x "
+                "1.965 GHz = 37.2 TFLOP/s",
+        "node_evals_per_s": my_insn / (dev_ms / args.steps * 1e-3),
+        "hbm_points_stream_GBps": (16.0 * n_points + h2d) / (dev_ms / args.steps * 1e-3) / 1e9,
+    }
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roof["hbm_peak_GBps_measured"] = peaks.get("hbm_gbs")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "expr-point evals/sec", "value": value, "unit": "expr-points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "population": pop_n, "points": n_points, "max_leafs": max_leafs,
+                   "sharding": args.shard, "generator_seed": SEED, "l2": "flushed between timed iterations (256 MiB memset)",
+                   "step": "score one full generation"},
+        "ms_per_generation": ms_per_step,
+        "e2e": {"value": e2e_value, "unit": "expr-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "clocks": clocks,
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+    }
+
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        sample = min(pop_n, args.cpu_sample)
+        b2 = cb.PopulationBuilder()
+        texts = b2.generate(SEED, sample, max_leafs, mix, want_texts=True)
+        t0 = time.perf_counter()
+        want, cores = O.score_batch(texts, xs, ys, max_leafs)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample * n_points / dt, "unit": "expr-points/s", "cores": cores, "kind": "port",
+                                "sample": "first %d of %d expressions x all %d points, once" % (sample, pop_n, n_points)}
+        if not by_points and lo == 0 and scores is not None:
+            m = min(sample, hi)
+            err = np.abs(scores[:m] - want[:m]) / np.maximum(1.0, np.abs(want[:m]))
+            line["parity_spot_check"] = {"expressions": int(m), "within_1e-9": float((err <= 1e-9).mean()),
+                                         "best_index_equal": bool(int(np.argmax(scores[:m])) == int(np.argmax(want[:m])))}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,11 +69,36 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     return s;
 }
 
+struct FullOut { double v0, v1, v2, v3; uint32_t nr, slow; };
+
+// the complete algebra on the lane's 4 points, one at a time: one small copy of the code, small register footprint
+__device__ __noinline__ FullOut full_chunk(const uint32_t *scode, const double *sconst, double x0, double x1, double x2,
+                                           double x3)
+{
+    FullOut o;
+    o.nr = 0;
+    o.slow = 0;
+    double v[4];
+    const double xs4[4] = { x0, x1, x2, x3 };
+#pragma unroll 1
+    for (int h = 0; h < 4; h++) {
+        const double xa[1] = { xs4[h] };
+        double re[1], im[1];
+        o.slow |= run_full<1>(scode, sconst, xa, re, im);
+        if (re[0] != re[0] || im[0] != 0.0) { o.nr |= 1u << h; re[0] = 0.0; }
+        v[h] = re[0];
+    }
+    o.v0 = v[0]; o.v1 = v[1]; o.v2 = v[2]; o.v3 = v[3];
+    return o;
+}
+
 // evaluates one 128-point chunk: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points whose value is
-// not a real number (eval.clj:70-80 turns those into +Inf).  Returns true when full semantics were needed.
+// not a real number (eval.clj:70-80 turns those into +Inf).  `mode` is the warp's adaptive state: 0 = try the
+// IEEE-real fast path first, 1 = go straight to the complete algebra (the previous chunk needed it).  Both
+// give bit-identical values wherever the fast path is valid, so the heuristic cannot change a score.
 __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool quirk, uint32_t quirk_off, int64_t base,
                                            int64_t n, const double *__restrict__ xs, double (&x)[4], double (&v)[4],
-                                           uint32_t &valid, uint32_t &nr)
+                                           uint32_t &valid, uint32_t &nr, uint32_t &mode)
 {
     valid = 0;
     nr = 0;
@@ -96,23 +121,20 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
         for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
         return false;
     }
-    uint32_t ev = run_real<4>(st.scode, st.sconst, x, v);
-    if (is_const) ev = 0xfu;
-    ev &= valid;
-    // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
+    if (mode == 0 && !is_const) {
+        uint32_t ev = run_real<4>(st.scode, st.sconst, x, v);
+        ev &= valid;
+        // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
-    nr &= valid;
-    if (!__any_sync(FULL, ev != 0)) return false;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if ((ev >> j) & 1u) {
-            const Z z = full_eval(st.scode, st.sconst, x[j]);
-            if (ztag(z) == T_REAL) v[j] = z.re;
-            else { v[j] = 0.0; nr |= 1u << j; }
-        }
+        for (int j = 0; j < 4; j++)
+            if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
+        nr &= valid;
+        if (!__any_sync(FULL, ev != 0)) return false;
     }
+    const FullOut o = full_chunk(st.scode, st.sconst, x[0], x[1], x[2], x[3]);
+    v[0] = o.v0; v[1] = o.v1; v[2] = o.v2; v[3] = o.v3;
+    nr = o.nr & valid;
+    mode = __any_sync(FULL, o.slow != 0) ? 1u : 0u;
     return true;
 }
 
@@ -153,14 +175,14 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
     if (c_hi > p.chunk_end) c_hi = p.chunk_end;
 
     double tile_max = 0.0;
-    uint32_t nonreal = 0;
+    uint32_t nonreal = 0, mode = 0;
     bool used_full = false;
     uint32_t cnt = 0;
     for (int64_t c = c_lo; c < c_hi; c++, cnt++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4], y[4];
         uint32_t valid, nr;
-        used_full |= eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr);
+        used_full |= eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode);
         if (base + 3 < p.n) {
             const double2 a = *reinterpret_cast<const double2 *>(p.ys + base);
             const double2 b = *reinterpret_cast<const double2 *>(p.ys + base + 2);
@@ -285,13 +307,13 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
     const uint32_t quirk_off = aux & 0xffffu;
     const int64_t nchunks = (p.n + CHUNK_POINTS - 1) / CHUNK_POINTS;
-    uint32_t nonreal = 0;
+    uint32_t nonreal = 0, mode = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t c = 0; c < nchunks; c++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4];
         uint32_t valid, nr;
-        eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr);
+        eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode);
         nonreal += __popc(nr);
 #pragma unroll
         for (int j = 0; j < 4; j++)
