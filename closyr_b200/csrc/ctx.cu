@@ -166,9 +166,10 @@ int check_population(closyr_ctx *ctx, const closyr_population *pop)
 // tile size (in chunks, power of two) so that the launch has enough warps to fill the GPU
 int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
 {
-    const int64_t target_items = 148 * 16 * 6;
+    const int64_t target_items = 148 * 4 * 6;          // CTAs of 4 warps, 4 resident per SM, a few waves
     int64_t cpt = pow2_ceil(std::max<int64_t>(1, nchunks));
-    while (cpt > 1 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;
+    while (cpt > MAX_CHUNKS_PER_TILE) cpt >>= 1;
+    while (cpt > 4 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;
     return (int32_t)cpt;
 }
 
@@ -197,7 +198,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.rflags = (uint8_t *)d.rflags.p;
     sp.partials = nullptr;
     sp.partial_tile_offset = 0;
-    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts);
+    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts, cpt);
     const bool direct = want_final && n_tiles == 1;
     sp.final_scores = direct ? 1 : 0;
     if (!direct) {
@@ -510,7 +511,7 @@ int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const doubl
     ep.n = n;
     ep.out_f = (double *)d.eval_f.p;
     ep.status = (uint8_t *)d.eval_status.p;
-    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts), d.stream);
+    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts, 0), d.stream);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     if (n) CU(ctx, cudaMemcpyAsync(out_f, d.eval_f.p, (size_t)(ne * n) * 8, cudaMemcpyDeviceToHost, d.stream));

@@ -1,10 +1,12 @@
 // kernels.cu -- sm_100a kernels of the scoring path.
 //
-// score_kernel: one warp (= one CTA) per (expression, tile of points).  The program and its constant pool are
-// staged in shared memory; lanes stride over the points, 4 consecutive points per lane per pass (two 16-byte
-// loads of xs and of ys per lane, a warp reads 1 KiB contiguous); the residuals are reduced with a fixed-shape
-// tree (lane-local left fold of 4, xor-butterfly over the warp, index-aligned binary tree over 128-point
-// chunks) so a score is bit-identical for every tiling, sharding and GPU count.  The epilogue reproduces
+// score_kernel: one CTA of SCORE_WARPS warps per (expression, tile of points).  The program and its constant
+// pool are staged once in shared memory and every warp of the CTA interprets it on different 128-point chunks
+// (so the warps of a CTA fetch the same instructions at about the same time: 4x fewer distinct instruction
+// streams per SM than one program per warp).  Lanes stride over the points, 4 consecutive points per lane per
+// pass (two 16-byte loads of xs and of ys per lane, a warp reads 1 KiB contiguous); the residuals are reduced
+// with a fixed-shape tree (lane-local left fold of 4, xor-butterfly over the warp, index-aligned binary tree
+// over the 128-point chunks) so a score is bit-identical for every tiling, sharding and GPU count.  The epilogue reproduces
 // closyr's formula operation by operation (reference src/closyr/ops.clj:78-116); the file is compiled with
 // -fmad=false so none of it is contracted.
 #include <cstdint>
@@ -19,6 +21,7 @@ using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_LEVELS = 40;
+constexpr int SCORE_WARPS = 4;       // warps per CTA = warps sharing one staged program
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -47,29 +50,29 @@ __device__ __forceinline__ double score_formula(double sum, double mx, int64_t n
 struct Staged {
     const uint32_t *scode;
     const double *sconst;
-    double *slvl;
+    double *slvl;      // per-chunk sums of the tile (score_kernel) / scratch
 };
 
-// copies one program into shared memory: [constants | levels | code (+1 word of slack)]
-__device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int lane)
+// copies one program into shared memory: [constants | `nlvl` doubles of scratch | code (+1 word of slack)]
+__device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
+                                                int nthreads, int nlvl)
 {
     const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
     const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
     const uint32_t ncode = c1 - c0, nk = k1 - k0;
     double *sconst = reinterpret_cast<double *>(smem);
     double *slvl = sconst + nk;
-    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + MAX_LEVELS);
+    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + nlvl);
     const double *gk = pop.consts + (k0 - pop.const_base);
     const uint32_t *gc = pop.code + (c0 - pop.code_base);
-    for (uint32_t i = lane; i < nk; i += 32) sconst[i] = gk[i];
-    for (uint32_t i = lane; i < ncode; i += 32) scode[i] = gc[i];
-    if (lane == 0) scode[ncode] = 0;
-    __syncwarp();
+    for (uint32_t i = tid; i < nk; i += nthreads) sconst[i] = gk[i];
+    for (uint32_t i = tid; i < ncode; i += nthreads) scode[i] = gc[i];
+    if (tid == 0) scode[ncode] = 0;
     Staged s = { scode, sconst, slvl };
     return s;
 }
 
-struct FullOut { double v0, v1, v2, v3; uint32_t nr, slow; };
+struct FullOut { double v0, v1, v2, v3; uint32_t nr; };
 
 // the complete algebra on the lane's 4 points, one at a time: one small copy of the code, small register footprint
 __device__ __noinline__ FullOut full_chunk(const uint32_t *scode, const double *sconst, double x0, double x1, double x2,
@@ -77,16 +80,14 @@ __device__ __noinline__ FullOut full_chunk(const uint32_t *scode, const double *
 {
     FullOut o;
     o.nr = 0;
-    o.slow = 0;
     double v[4];
     const double xs4[4] = { x0, x1, x2, x3 };
 #pragma unroll 1
     for (int h = 0; h < 4; h++) {
-        const double xa[1] = { xs4[h] };
-        double re[1], im[1];
-        o.slow |= run_full<1>(scode, sconst, xa, re, im);
-        if (re[0] != re[0] || im[0] != 0.0) { o.nr |= 1u << h; re[0] = 0.0; }
-        v[h] = re[0];
+        const Z z = run_full(scode, sconst, xs4[h]);
+        const bool real = z.re == z.re && z.im == 0.0;
+        if (!real) o.nr |= 1u << h;
+        v[h] = real ? z.re : 0.0;
     }
     o.v0 = v[0]; o.v1 = v[1]; o.v2 = v[2]; o.v3 = v[3];
     return o;
@@ -134,14 +135,16 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
     const FullOut o = full_chunk(st.scode, st.sconst, x[0], x[1], x[2], x[3]);
     v[0] = o.v0; v[1] = o.v1; v[2] = o.v2; v[3] = o.v3;
     nr = o.nr & valid;
-    mode = __any_sync(FULL, o.slow != 0) ? 1u : 0u;
+    mode = __any_sync(FULL, nr != 0) ? 1u : 0u;    // stay with the complete algebra while it keeps finding non-real points
     return true;
 }
 
-__global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(SCORE_WARPS * 32, 4) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x;
+    __shared__ double s_max[SCORE_WARPS];
+    __shared__ uint32_t s_nonreal[SCORE_WARPS], s_full[SCORE_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t item = blockIdx.x;
     const int64_t e = item / p.n_tiles;
     const int tile = (int)(item - e * p.n_tiles);
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
     const bool too_big = leafs > p.max_leafs;                               // ops.clj:128-129
     const bool dead = (flags & (CL_F_UNSUPPORTED | CL_F_NIL)) != 0;        // eval nil / unsupported => min-score
     if (too_big || dead || p.n <= 0) {
-        if (lane == 0) {
+        if (tid == 0) {
             if (p.final_scores) {
                 p.scores[e] = CLOSYR_MIN_SCORE;
                 p.rflags[e] = too_big ? CL_R_TOO_BIG : CL_R_MIN_SCORE;
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
         return;
     }
 
-    const Staged st = stage_program(p.pop, e, smem, lane);
+    const Staged st = stage_program(p.pop, e, smem, tid, SCORE_WARPS * 32, p.chunks_per_tile);
+    __syncthreads();
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -173,12 +177,12 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
     const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
     int64_t c_hi = c_lo + p.chunks_per_tile;
     if (c_hi > p.chunk_end) c_hi = p.chunk_end;
+    const int cnt = (int)(c_hi - c_lo);
 
-    double tile_max = 0.0;
+    double warp_mx = 0.0;
     uint32_t nonreal = 0, mode = 0;
     bool used_full = false;
-    uint32_t cnt = 0;
-    for (int64_t c = c_lo; c < c_hi; c++, cnt++) {
+    for (int64_t c = c_lo + warp; c < c_hi; c += SCORE_WARPS) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4], y[4];
         uint32_t valid, nr;
@@ -203,30 +207,34 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
         }
         nonreal += __popc(nr);
         s = warp_sum(s);
-        tile_max = fmax(tile_max, m);
-        // streaming pairwise insertion: level k holds the sum of an aligned block of 2^k chunks
-        uint32_t k = 0;
-        for (uint32_t t = cnt; t & 1u; t >>= 1, k++) s = st.slvl[k] + s;
-        __syncwarp();
-        if (lane == 0) st.slvl[k] = s;
-        __syncwarp();
+        warp_mx = fmax(warp_mx, m);
+        if (lane == 0) st.slvl[c - c_lo] = s;                  // the chunk's residual sum, leaf of the tree
     }
-    double tile_sum = 0.0;
-    bool have = false;
-    for (uint32_t k = 0; (cnt >> k) != 0; k++) {
-        if ((cnt >> k) & 1u) {
-            tile_sum = have ? st.slvl[k] + tile_sum : st.slvl[k];
-            have = true;
-        }
-    }
-    tile_max = warp_max(tile_max);
+    warp_mx = warp_max(warp_mx);
     nonreal = __reduce_add_sync(FULL, nonreal);
+    if (lane == 0) { s_max[warp] = warp_mx; s_nonreal[warp] = nonreal; s_full[warp] = used_full ? 1u : 0u; }
+    __syncthreads();
+    if (warp != 0) return;
 
+    // index-aligned pairwise tree over the chunk sums (a missing right child leaves the left one unchanged)
+    for (int stride = 1; stride < cnt; stride <<= 1) {
+        for (int i = lane * 2 * stride; i + stride < cnt; i += 64 * stride) st.slvl[i] = st.slvl[i] + st.slvl[i + stride];
+        __syncwarp();
+    }
     if (lane != 0) return;
+    const double tile_sum = cnt > 0 ? st.slvl[0] : 0.0;
+    double tile_max = 0.0;
+    uint32_t tile_nonreal = 0, tile_full = 0;
+#pragma unroll
+    for (int w = 0; w < SCORE_WARPS; w++) {
+        tile_max = fmax(tile_max, s_max[w]);
+        tile_nonreal += s_nonreal[w];
+        tile_full |= s_full[w];
+    }
     if (p.final_scores) {
-        uint8_t rf = used_full ? CL_R_FULL_SEMANTICS : 0;
+        uint8_t rf = tile_full ? CL_R_FULL_SEMANTICS : 0;
         double score;
-        if (is_const && !quirk && nonreal != 0) {                     // eval.clj:83-96 throws => min-score
+        if (is_const && !quirk && tile_nonreal != 0) {                 // eval.clj:83-96 throws => min-score
             score = CLOSYR_MIN_SCORE;
             rf |= CL_R_MIN_SCORE;
         } else score = score_formula(tile_sum, tile_max, p.n, leafs);
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(32) score_kernel(const ScoreParams p)
         double *out = p.partials + ((p.partial_tile_offset + tile) * p.pop.n_expr + e) * 3;
         out[0] = tile_sum;
         out[1] = tile_max;
-        out[2] = (double)nonreal + (used_full ? 0.25 : 0.0);          // fraction carries the diagnostic bit
+        out[2] = (double)tile_nonreal + (tile_full ? 0.25 : 0.0);     // fraction carries the diagnostic bit
     }
 }
 
@@ -301,7 +309,8 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
         if (lane == 0) p.status[e] = 1;
         return;
     }
-    const Staged st = stage_program(p.pop, e, smem, lane);
+    const Staged st = stage_program(p.pop, e, smem, lane, 32, 0);
+    __syncwarp();
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -387,7 +396,7 @@ void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
 {
     const int64_t items = p.pop.n_expr * p.n_tiles;
     if (items <= 0) return;
-    score_kernel<<<(unsigned)items, 32, smem_bytes, (cudaStream_t)stream>>>(p);
+    score_kernel<<<(unsigned)items, SCORE_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(p);
 }
 
 void launch_finalize(const FinalizeParams &p, void *stream)
@@ -413,9 +422,9 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
     fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
 }
 
-size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts)
+size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile)
 {
-    return (size_t)max_consts * 8 + MAX_LEVELS * 8 + ((size_t)max_code_words + 1) * 4 + 16;
+    return (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 + ((size_t)max_code_words + 1) * 4 + 16;
 }
 
 }  // namespace closyr

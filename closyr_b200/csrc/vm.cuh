@@ -32,39 +32,62 @@ __device__ __forceinline__ bool is_integer_value(double y) { return !nonfinite(y
 
 // ------------------------------------------------------------------------------------------------
 // single-copy math.  Every warp runs a different program, so the interpreter jumps between routines all the
-// time: the whole kernel image has to stay close to the instruction cache (32 KB L1.5 per SM).  Each libdevice
-// routine therefore exists exactly once, behind a call, instead of being inlined at every use
-// (inlined per point and per interpreter the kernel was 300 KB of SASS and stalled on instruction fetch).
+// time and the hot part of the kernel image has to fit the instruction cache (first version: every libdevice
+// routine inlined per point and per interpreter = 300 KB of SASS, 46 of 47 warp-cycles stalled on
+// instruction fetch).  Hence ONE entry point for every real elementary function, called per point; each
+// libdevice routine exists exactly once in the image, and both interpreters and the complex algebra use it.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ double k_sin(double x) { return sin(x); }
-__device__ __noinline__ double k_cos(double x) { return cos(x); }
-__device__ __noinline__ double k_tan(double x) { return tan(x); }
-__device__ __noinline__ double k_exp(double x) { return exp(x); }
-__device__ __noinline__ double k_log(double x) { return log(x); }
-__device__ __noinline__ double k_asin(double x) { return asin(x); }
-__device__ __noinline__ double k_acos(double x) { return acos(x); }
-__device__ __noinline__ double k_pow(double x, double y) { return pow(x, y); }
-__device__ __noinline__ double k_sinh(double x) { return sinh(x); }
-__device__ __noinline__ double k_cosh(double x) { return cosh(x); }
-__device__ __noinline__ double k_hypot(double x, double y) { return hypot(x, y); }
-__device__ __noinline__ double k_atan2(double y, double x) { return atan2(y, x); }
-
-// integer power by square-and-multiply, MSB first (the same chain the oracle walks)
+// integer power by square-and-multiply, MSB first (the same chain the oracle walks); n != 0
 __device__ __forceinline__ double powi_real(double a, int n)
 {
     unsigned m = (unsigned)(n < 0 ? -n : n);
     int top = 31 - __clz((int)m);
     double r = a;
+#pragma unroll 1
     for (int b = top - 1; b >= 0; b--) {
         r = r * r;
         if ((m >> b) & 1u) r = r * a;
     }
     return n < 0 ? 1.0 / r : r;
 }
-__device__ __noinline__ double k_recip(double x) { return 1.0 / x; }
-__device__ __noinline__ double k_sqrt(double x) { return sqrt(x); }
-__device__ __noinline__ double k_rsqrt(double x) { return 1.0 / sqrt(x); }
-__device__ __noinline__ double k_powi(double x, int n) { return powi_real(x, n); }
+
+enum { U_SINH = 100, U_COSH = 101 };
+
+// real elementary function `op` of a (c = the literal operand of POWI / POWC)
+__device__ __noinline__ double u_real(uint32_t op, double a, double c)
+{
+    switch (op) {
+    case CL_RECIP: return 1.0 / a;
+    case CL_SQRT: return sqrt(a);
+    case CL_RSQRT: return 1.0 / sqrt(a);
+    case CL_POWI: return powi_real(a, (int)c);
+    case CL_POWC: return pow(a, c);
+    case CL_EXP: return exp(a);
+    case CL_LOG: return log(a);
+    case CL_SIN: return sin(a);
+    case CL_COS: return cos(a);
+    case CL_TAN: return tan(a);
+    case CL_ASIN: return asin(a);
+    case CL_ACOS: return acos(a);
+    case U_SINH: return sinh(a);
+    case U_COSH: return cosh(a);
+    default: return fabs(a);            // CL_ABS
+    }
+}
+#define k_sin(x) u_real(CL_SIN, (x), 0.0)
+#define k_cos(x) u_real(CL_COS, (x), 0.0)
+#define k_tan(x) u_real(CL_TAN, (x), 0.0)
+#define k_exp(x) u_real(CL_EXP, (x), 0.0)
+#define k_log(x) u_real(CL_LOG, (x), 0.0)
+#define k_asin(x) u_real(CL_ASIN, (x), 0.0)
+#define k_acos(x) u_real(CL_ACOS, (x), 0.0)
+#define k_pow(x, y) u_real(CL_POWC, (x), (y))
+#define k_sinh(x) u_real(U_SINH, (x), 0.0)
+#define k_cosh(x) u_real(U_COSH, (x), 0.0)
+#define k_recip(x) u_real(CL_RECIP, (x), 0.0)
+#define k_sqrt(x) u_real(CL_SQRT, (x), 0.0)
+__device__ __noinline__ double k_hypot(double x, double y) { return hypot(x, y); }
+__device__ __noinline__ double k_atan2(double y, double x) { return atan2(y, x); }
 
 // ------------------------------------------------------------------------------------------------
 // full value algebra
@@ -342,146 +365,86 @@ __device__ __noinline__ Z zpow(Z z, Z w)
 }
 
 // ------------------------------------------------------------------------------------------------
-// complete value algebra, P points per lane.  Values are (re, im) register pairs; im == 0 means "on the real
-// line" (including directed infinities; Indeterminate is re = NaN), and for such operands every instruction
-// takes the same IEEE instruction sequence as run_real, inline.  Anything else (complex numbers,
-// ComplexInfinity, poles, domain exits) goes through the scalar z* functions above.  `slow` collects whether
-// any point left the inline path, so the caller can drop back to run_real for the next chunk.
+// complete value algebra, one instruction applied to one value.  On the real line (im == 0: finite reals,
+// directed infinities, and Indeterminate as re = NaN) an instruction takes the same IEEE sequence as the fast
+// path whenever that is the algebra's answer; poles, domain exits and genuinely complex operands go to z*.
 // ------------------------------------------------------------------------------------------------
-#define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
-#define CLOSYR_Z(j) zv(re[j], im[j])
-#define CLOSYR_SETZ(j, expr) { const Z z_ = (expr); re[j] = z_.re; im[j] = z_.im; slow = 1u; }
-// unary instruction: `cond` says the point may take the real instruction sequence `fast`
-#define CLOSYR_UNARY(cond, fast, slowf)                                           \
-    CLOSYR_FORJ {                                                                 \
-        const double a_ = re[j];                                                  \
-        if (im[j] == 0.0 && (cond)) re[j] = (fast);                               \
-        else CLOSYR_SETZ(j, slowf(CLOSYR_Z(j)))                                   \
-    }
-
-template <int P>
-__device__ __forceinline__ uint32_t run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
-                                             const double (&x)[P], double (&re)[P], double (&im)[P])
+__device__ __noinline__ Z u_full(uint32_t op, Z a, double c)
 {
-    double s0r[P], s0i[P], s1r[P], s1i[P], s2r[P], s2i[P], s3r[P], s3i[P];
-    Z ls[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];       // deep spill slots (local memory, rarely touched)
-    uint32_t slow = 0;
-    int pc = 0;
-    uint32_t w = scode[0];
-    CLOSYR_FORJ {
-        re[j] = 0.0; im[j] = 0.0;
-        s0r[j] = s0i[j] = s1r[j] = s1i[j] = s2r[j] = s2i[j] = s3r[j] = s3i[j] = 0.0;
+    if (a.im == 0.0) {
+        const double x = a.re;
+        switch (op) {
+        case CL_NEG: return zv(-x, 0.0);
+        case CL_SQR: return zv(x * x, 0.0);
+        case CL_RECIP: if (x != 0.0) return zv(k_recip(x), 0.0); break;
+        case CL_SQRT: if (x >= 0.0) return zv(k_sqrt(x), 0.0); break;
+        case CL_RSQRT: if (x > 0.0) return zv(u_real(CL_RSQRT, x, 0.0), 0.0); break;
+        case CL_POWI: {
+            const int n = (int)c;
+            const double r = u_real(CL_POWI, x, n < 0 ? -c : c);
+            if (n > 0) return zv(r, 0.0);
+            if (r != 0.0) return zv(k_recip(r), 0.0);
+            return zcinf();
+        }
+        case CL_POWC: if (x > 0.0 && !is_inf(x) && !nonfinite(c) && c != 0.0) return zv(k_pow(x, c), 0.0); break;
+        case CL_LOG: if (x > 0.0) return zv(k_log(x), 0.0); break;
+        case CL_ASIN:
+        case CL_ACOS: if (fabs(x) <= 1.0) return zv(u_real(op, x, 0.0), 0.0); break;
+        default: return zv(u_real(op, x, 0.0), 0.0);      // EXP SIN COS TAN ABS: total on the real line
+        }
     }
-#define CLOSYR_ST(sr, si) CLOSYR_FORJ { sr[j] = re[j]; si[j] = im[j]; }
-#define CLOSYR_BIN(sr, si, op, slowf)                                             \
-    CLOSYR_FORJ {                                                                 \
-        if (im[j] == 0.0 && si[j] == 0.0) re[j] = sr[j] op re[j];                 \
-        else CLOSYR_SETZ(j, slowf(zv(sr[j], si[j]), CLOSYR_Z(j)))                 \
+    switch (op) {
+    case CL_NEG: return zneg(a);
+    case CL_SQR: return zmul(a, a);
+    case CL_RECIP: return zrecip(a);
+    case CL_SQRT: return zsqrt(a);
+    case CL_RSQRT: return zrecip(zsqrt(a));
+    case CL_POWI: return zpowi(a, (int)c);
+    case CL_POWC: return zpow(a, zmk(c, 0.0));
+    case CL_EXP: return zexp(a);
+    case CL_LOG: return zlog(a);
+    case CL_SIN: return zsin(a);
+    case CL_COS: return zcos(a);
+    case CL_TAN: return ztan(a);
+    case CL_ASIN: return zasin(a);
+    case CL_ACOS: return zacos(a);
+    default: return zabs(a);
     }
-    for (;;) {
+}
+
+// One point through the program with the complete algebra.  Deliberately compact (one copy of everything,
+// slots in a small local array): it only runs for the 128-point chunks the fast path reported.
+__device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x)
+{
+    Z slot[CLOSYR_MAX_SLOTS];
+    Z acc = zv(0.0, 0.0);
+#pragma unroll 1
+    for (int pc = 0;; pc++) {
+        const uint32_t w = scode[pc];
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
-        w = scode[++pc];
-        switch (op) {
-        case CL_END: return slow;
-        case CL_LDX: CLOSYR_FORJ { re[j] = x[j]; im[j] = 0.0; } break;
-        case CL_LDC: { const double c = sconst[b]; CLOSYR_FORJ { re[j] = c; im[j] = 0.0; } break; }
-        case CL_LDZ: { const Z c = zmk(sconst[b], sconst[b + 1]); CLOSYR_FORJ { re[j] = c.re; im[j] = c.im; } slow = 1u; break; }
-        case CL_LDSPEC: { const Z c = a == 0 ? zcinf() : zindet(); CLOSYR_FORJ { re[j] = c.re; im[j] = c.im; } slow = 1u; break; }
-        case CL_ADDX:
-            CLOSYR_FORJ { if (im[j] == 0.0) re[j] = re[j] + x[j]; else CLOSYR_SETZ(j, zadd(CLOSYR_Z(j), zv(x[j], 0.0))) }
-            break;
-        case CL_ADDC: {
-            const double c = sconst[b];
-            CLOSYR_FORJ { if (im[j] == 0.0) re[j] = re[j] + c; else CLOSYR_SETZ(j, zadd(CLOSYR_Z(j), zv(c, 0.0))) }
-            break;
-        }
-        case CL_MULX:
-            CLOSYR_FORJ { if (im[j] == 0.0) re[j] = re[j] * x[j]; else CLOSYR_SETZ(j, zmul(CLOSYR_Z(j), zv(x[j], 0.0))) }
-            break;
-        case CL_MULC: {
-            const double c = sconst[b];
-            CLOSYR_FORJ { if (im[j] == 0.0) re[j] = re[j] * c; else CLOSYR_SETZ(j, zmul(CLOSYR_Z(j), zv(c, 0.0))) }
-            break;
-        }
-        case CL_NEG: CLOSYR_UNARY(true, -a_, zneg) break;
-        case CL_RECIP: CLOSYR_UNARY(a_ != 0.0, k_recip(a_), zrecip) break;
-        case CL_SQR: CLOSYR_FORJ { if (im[j] == 0.0) re[j] = re[j] * re[j]; else CLOSYR_SETZ(j, zmul(CLOSYR_Z(j), CLOSYR_Z(j))) } break;
-        case CL_SQRT: CLOSYR_UNARY(a_ >= 0.0, k_sqrt(a_), zsqrt) break;
-        case CL_RSQRT:
-            CLOSYR_FORJ {
-                const double a_ = re[j];
-                if (im[j] == 0.0 && a_ > 0.0) re[j] = k_rsqrt(a_);
-                else CLOSYR_SETZ(j, zrecip(zsqrt(CLOSYR_Z(j))))
+        if (op == CL_END) return acc;
+        if (op <= CL_LDSPEC) {
+            acc = op == CL_LDX ? zv(x, 0.0) : op == CL_LDC ? zv(sconst[b], 0.0)
+                : op == CL_LDZ ? zmk(sconst[b], sconst[b + 1]) : a == 0 ? zcinf() : zindet();
+        } else if (op <= CL_MULC) {
+            const double c = (op == CL_ADDX || op == CL_MULX) ? x : sconst[b];
+            if (acc.im == 0.0) acc.re = op <= CL_ADDC ? acc.re + c : acc.re * c;
+            else acc = op <= CL_ADDC ? zadd(acc, zv(c, 0.0)) : zmul(acc, zv(c, 0.0));
+        } else if (op < CL_ST) {
+            acc = u_full(op, acc, op == CL_POWC ? sconst[b] : (double)(short)b);
+        } else {
+            // slot instructions: a is the slot for both the generic and the register forms
+            const uint32_t kind = op >= CL_MULS0 ? CL_MULS : op >= CL_ADDS0 ? CL_ADDS : op >= CL_ST0 ? CL_ST : op;
+            if (kind == CL_ST) slot[a] = acc;
+            else {
+                const Z sl = slot[a];
+                if (kind == CL_POWS) acc = zpow(sl, acc);
+                else if (sl.im == 0.0 && acc.im == 0.0) acc.re = kind == CL_ADDS ? sl.re + acc.re : sl.re * acc.re;
+                else acc = kind == CL_ADDS ? zadd(sl, acc) : zmul(sl, acc);
             }
-            break;
-        case CL_POWI: {
-            const int n = (int)(short)b;
-            CLOSYR_FORJ {
-                if (im[j] == 0.0) {
-                    const double r = k_powi(re[j], n < 0 ? -n : n);
-                    if (n > 0) re[j] = r;
-                    else if (r != 0.0) re[j] = k_recip(r);
-                    else CLOSYR_SETZ(j, zcinf())
-                } else CLOSYR_SETZ(j, zpowi(CLOSYR_Z(j), n))
-            }
-            break;
-        }
-        case CL_POWC: {
-            const double y = sconst[b];
-            const bool plain = !nonfinite(y) && y != 0.0;
-            CLOSYR_FORJ {
-                const double a_ = re[j];
-                if (plain && im[j] == 0.0 && a_ > 0.0 && !is_inf(a_)) re[j] = k_pow(a_, y);
-                else CLOSYR_SETZ(j, zpow(CLOSYR_Z(j), zmk(y, 0.0)))
-            }
-            break;
-        }
-        case CL_EXP: CLOSYR_UNARY(true, k_exp(a_), zexp) break;
-        case CL_LOG: CLOSYR_UNARY(a_ > 0.0, k_log(a_), zlog) break;
-        case CL_SIN: CLOSYR_UNARY(true, k_sin(a_), zsin) break;
-        case CL_COS: CLOSYR_UNARY(true, k_cos(a_), zcos) break;
-        case CL_TAN: CLOSYR_UNARY(true, k_tan(a_), ztan) break;
-        case CL_ASIN: CLOSYR_UNARY(fabs(a_) <= 1.0, k_asin(a_), zasin) break;
-        case CL_ACOS: CLOSYR_UNARY(fabs(a_) <= 1.0, k_acos(a_), zacos) break;
-        case CL_ABS: CLOSYR_UNARY(true, fabs(a_), zabs) break;
-        case CL_ST0 + 0: CLOSYR_ST(s0r, s0i) break;
-        case CL_ST0 + 1: CLOSYR_ST(s1r, s1i) break;
-        case CL_ST0 + 2: CLOSYR_ST(s2r, s2i) break;
-        case CL_ST0 + 3: CLOSYR_ST(s3r, s3i) break;
-        case CL_ADDS0 + 0: CLOSYR_BIN(s0r, s0i, +, zadd) break;
-        case CL_ADDS0 + 1: CLOSYR_BIN(s1r, s1i, +, zadd) break;
-        case CL_ADDS0 + 2: CLOSYR_BIN(s2r, s2i, +, zadd) break;
-        case CL_ADDS0 + 3: CLOSYR_BIN(s3r, s3i, +, zadd) break;
-        case CL_MULS0 + 0: CLOSYR_BIN(s0r, s0i, *, zmul) break;
-        case CL_MULS0 + 1: CLOSYR_BIN(s1r, s1i, *, zmul) break;
-        case CL_MULS0 + 2: CLOSYR_BIN(s2r, s2i, *, zmul) break;
-        case CL_MULS0 + 3: CLOSYR_BIN(s3r, s3i, *, zmul) break;
-        default: {
-            // generic slot forms (deep slots) and the general power: scalar algebra throughout
-            CLOSYR_FORJ {
-                Z sl = zv(0.0, 0.0);
-                if (op != CL_ST) {
-                    if (a >= CLOSYR_REG_SLOTS) sl = ls[a - CLOSYR_REG_SLOTS][j];
-                    else sl = a == 0 ? zv(s0r[j], s0i[j]) : a == 1 ? zv(s1r[j], s1i[j]) : a == 2 ? zv(s2r[j], s2i[j]) : zv(s3r[j], s3i[j]);
-                }
-                if (op == CL_ST) {
-                    if (a >= CLOSYR_REG_SLOTS) ls[a - CLOSYR_REG_SLOTS][j] = CLOSYR_Z(j);
-                    else if (a == 0) { s0r[j] = re[j]; s0i[j] = im[j]; }
-                    else if (a == 1) { s1r[j] = re[j]; s1i[j] = im[j]; }
-                    else if (a == 2) { s2r[j] = re[j]; s2i[j] = im[j]; }
-                    else { s3r[j] = re[j]; s3i[j] = im[j]; }
-                } else if (op == CL_ADDS) CLOSYR_SETZ(j, zadd(sl, CLOSYR_Z(j)))
-                else if (op == CL_MULS) CLOSYR_SETZ(j, zmul(sl, CLOSYR_Z(j)))
-                else if (op == CL_POWS) CLOSYR_SETZ(j, zpow(sl, CLOSYR_Z(j)))
-                else CLOSYR_SETZ(j, zindet())
-            }
-            break;
-        }
         }
     }
-#undef CLOSYR_ST
-#undef CLOSYR_BIN
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,19 +453,12 @@ __device__ __forceinline__ uint32_t run_full(const uint32_t *__restrict__ scode,
 // Invariant kept per point (v = the IEEE value here, s = the value of the full algebra):
 //   v finite  <=>  s is a finite real and v == s;   v = +-Inf  =>  s is ComplexInfinity or a directed infinity
 //   (IEEE cannot tell which);   v NaN, no event  =>  s is Indeterminate (absorbing: the point is not real).
-// The returned mask has bit j set when point j must be re-evaluated by full_eval because the invariant
-// cannot be kept:  (1) a function left its real domain (NaN out of a non-NaN input: the full algebra
-// continues over the complex numbers or with ComplexInfinity);  (2) an infinity reaches an instruction that
-// can turn it into a finite number (1/Inf = 0, E^-Inf = 0, Inf^-y = 0) -- whether that is right depends on
-// which infinity it was;  (3) literals that are not real, and general x^y.
+// The returned mask has bit j set when point j must be re-evaluated with the complete algebra because the
+// invariant cannot be kept: an elementary function (anything but + * neg square) produced NaN from a non-NaN
+// input (it left its real domain: the algebra continues over the complex numbers) or was handed an infinity
+// (1/Inf = 0, E^-Inf = 0 ... are only right for some infinities); literals that are not real; general x^y.
 // ------------------------------------------------------------------------------------------------
-#define CLOSYR_DOMAIN_OP(expr)                                                 \
-    CLOSYR_FORJ {                                                              \
-        const double in_ = acc[j];                                             \
-        const double r_ = (expr);                                              \
-        if (r_ != r_ && in_ == in_) ev |= 1u << j;                             \
-        acc[j] = r_;                                                           \
-    }
+#define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
 
 template <int P>
 __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
@@ -514,6 +470,7 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
     int pc = 0;
     uint32_t w = scode[0];
     CLOSYR_FORJ { acc[j] = 0.0; s0[j] = 0.0; s1[j] = 0.0; s2[j] = 0.0; s3[j] = 0.0; }
+#pragma unroll 1
     for (;;) {
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
@@ -522,38 +479,12 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
         case CL_END: return ev;
         case CL_LDX: CLOSYR_FORJ acc[j] = x[j]; break;
         case CL_LDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = c; break; }
-        case CL_LDZ:
-        case CL_LDSPEC: ev = (1u << P) - 1u; break;
         case CL_ADDX: CLOSYR_FORJ acc[j] = acc[j] + x[j]; break;
         case CL_ADDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] + c; break; }
         case CL_MULX: CLOSYR_FORJ acc[j] = acc[j] * x[j]; break;
         case CL_MULC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] * c; break; }
         case CL_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;
-        case CL_RECIP: CLOSYR_FORJ { if (is_inf(acc[j])) ev |= 1u << j; acc[j] = k_recip(acc[j]); } break;
         case CL_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
-        case CL_SQRT: CLOSYR_DOMAIN_OP(k_sqrt(in_)) break;
-        case CL_RSQRT: CLOSYR_DOMAIN_OP(is_inf(in_) ? __longlong_as_double(0x7ff8000000000000ll) : k_rsqrt(in_)) break;
-        case CL_POWI: {
-            const int n = (int)(short)b;
-            CLOSYR_FORJ { if (n < 0 && is_inf(acc[j])) ev |= 1u << j; acc[j] = k_powi(acc[j], n); }
-            break;
-        }
-        case CL_POWC: {
-            const double y = sconst[b];
-            if (nonfinite(y) || y == 0.0) { ev = (1u << P) - 1u; break; }
-            CLOSYR_DOMAIN_OP(is_inf(in_) ? __longlong_as_double(0x7ff8000000000000ll) : k_pow(in_, y))
-            break;
-        }
-        case CL_EXP:
-            CLOSYR_FORJ { if (is_inf(acc[j])) ev |= 1u << j; acc[j] = k_exp(acc[j]); }
-            break;
-        case CL_LOG: CLOSYR_DOMAIN_OP(k_log(in_)) break;
-        case CL_SIN: CLOSYR_FORJ acc[j] = k_sin(acc[j]); break;
-        case CL_COS: CLOSYR_FORJ acc[j] = k_cos(acc[j]); break;
-        case CL_TAN: CLOSYR_FORJ acc[j] = k_tan(acc[j]); break;
-        case CL_ASIN: CLOSYR_DOMAIN_OP(k_asin(in_)) break;
-        case CL_ACOS: CLOSYR_DOMAIN_OP(k_acos(in_)) break;
-        case CL_ABS: CLOSYR_FORJ acc[j] = fabs(acc[j]); break;
         case CL_ST0 + 0: CLOSYR_FORJ s0[j] = acc[j]; break;
         case CL_ST0 + 1: CLOSYR_FORJ s1[j] = acc[j]; break;
         case CL_ST0 + 2: CLOSYR_FORJ s2[j] = acc[j]; break;
@@ -578,10 +509,24 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
             if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ acc[j] = ls[a - CLOSYR_REG_SLOTS][j] * acc[j]; }
             else ev = (1u << P) - 1u;
             break;
-        case CL_POWS:
-        default:
-            ev = (1u << P) - 1u;       // general x^y (dormant crossover flavours only): full semantics decide
+        case CL_LDZ:
+        case CL_LDSPEC:
+        case CL_POWS: ev = (1u << P) - 1u; break;
+        default: {
+            // every other instruction is a real elementary function of the accumulator
+            double c = (double)(short)b;
+            if (op == CL_POWC) {
+                c = sconst[b];
+                if (nonfinite(c) || c == 0.0) { ev = (1u << P) - 1u; break; }
+            }
+            CLOSYR_FORJ {
+                const double in_ = acc[j];
+                const double r_ = u_real(op, in_, c);
+                if (is_inf(in_) || (r_ != r_ && in_ == in_)) ev |= 1u << j;
+                acc[j] = r_;
+            }
             break;
+        }
         }
     }
 }
