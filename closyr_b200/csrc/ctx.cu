@@ -198,7 +198,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.rflags = (uint8_t *)d.rflags.p;
     sp.partials = nullptr;
     sp.partial_tile_offset = 0;
-    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts, cpt);
+    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts, cpt, score_warps());
     const bool direct = want_final && n_tiles == 1;
     sp.final_scores = direct ? 1 : 0;
     if (!direct) {
@@ -511,7 +511,7 @@ int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const doubl
     ep.n = n;
     ep.out_f = (double *)d.eval_f.p;
     ep.status = (uint8_t *)d.eval_status.p;
-    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts, 0), d.stream);
+    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts, 0, 1), d.stream);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     if (n) CU(ctx, cudaMemcpyAsync(out_f, d.eval_f.p, (size_t)(ne * n) * 8, cudaMemcpyDeviceToHost, d.stream));

@@ -51,16 +51,20 @@ struct Staged {
     const uint32_t *scode;
     const double *sconst;
     double *slvl;      // per-chunk sums of the tile (score_kernel) / scratch
+    double *sslot;     // this lane's column of the warp's spill slots: [slot 0..3][point 0..3][lane]
 };
 
-// copies one program into shared memory: [constants | `nlvl` doubles of scratch | code (+1 word of slack)]
+constexpr int SLOT_DOUBLES_PER_WARP = CLOSYR_REG_SLOTS * POINTS_PER_LANE * 32;
+
+// copies one program into shared memory: [warp slots | constants | `nlvl` doubles of scratch | code (+1 word)]
 __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
                                                 int nthreads, int nlvl)
 {
     const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
     const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
     const uint32_t ncode = c1 - c0, nk = k1 - k0;
-    double *sconst = reinterpret_cast<double *>(smem);
+    double *sslot = reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31);
+    double *sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
     double *slvl = sconst + nk;
     uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + nlvl);
     const double *gk = pop.consts + (k0 - pop.const_base);
@@ -68,7 +72,7 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     for (uint32_t i = tid; i < nk; i += nthreads) sconst[i] = gk[i];
     for (uint32_t i = tid; i < ncode; i += nthreads) scode[i] = gc[i];
     if (tid == 0) scode[ncode] = 0;
-    Staged s = { scode, sconst, slvl };
+    Staged s = { scode, sconst, slvl, sslot };
     return s;
 }
 
@@ -123,7 +127,7 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
         return false;
     }
     if (mode == 0 && !is_const) {
-        uint32_t ev = run_real<4>(st.scode, st.sconst, x, v);
+        uint32_t ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v);
         ev &= valid;
         // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
 #pragma unroll
@@ -422,9 +426,11 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
     fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
 }
 
-size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile)
+size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps)
 {
-    return (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 + ((size_t)max_code_words + 1) * 4 + 16;
+    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 +
+           ((size_t)max_code_words + 1) * 4 + 16;
 }
+int score_warps() { return SCORE_WARPS; }
 
 }  // namespace closyr

@@ -460,21 +460,31 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
 // ------------------------------------------------------------------------------------------------
 #define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
 
+// Loop-carried state is only the accumulator (P doubles); x is loaded once per chunk.  The spill slots live
+// in shared memory ([slot][point][lane], conflict-free): with slots in registers the compiler copied the whole
+// 40-register state at every dispatch (36 % of all issued instructions were IMAD.MOV, ncu profile r01_c).
 template <int P>
 __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
-                                             const double (&x)[P], double (&acc)[P])
+                                             double *__restrict__ sslot, const double (&x)[P], double (&acc)[P])
 {
-    double s0[P], s1[P], s2[P], s3[P];
     double ls[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];    // deep spill slots: local memory, rarely touched
     uint32_t ev = 0;
     int pc = 0;
     uint32_t w = scode[0];
-    CLOSYR_FORJ { acc[j] = 0.0; s0[j] = 0.0; s1[j] = 0.0; s2[j] = 0.0; s3[j] = 0.0; }
+    CLOSYR_FORJ acc[j] = 0.0;
 #pragma unroll 1
     for (;;) {
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
         w = scode[++pc];                                     // prefetch (the buffer has one word of slack)
+        if (op >= CL_ST0) {
+            // register-file-free slot forms: CL_ST0+a, CL_ADDS0+a, CL_MULS0+a with a in 0..3
+            double *sl = sslot + a * (P * 32);
+            if (op < CL_ADDS0) { CLOSYR_FORJ sl[j * 32] = acc[j]; }
+            else if (op < CL_MULS0) { CLOSYR_FORJ acc[j] = sl[j * 32] + acc[j]; }
+            else { CLOSYR_FORJ acc[j] = sl[j * 32] * acc[j]; }
+            continue;
+        }
         switch (op) {
         case CL_END: return ev;
         case CL_LDX: CLOSYR_FORJ acc[j] = x[j]; break;
@@ -485,18 +495,6 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
         case CL_MULC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] * c; break; }
         case CL_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;
         case CL_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
-        case CL_ST0 + 0: CLOSYR_FORJ s0[j] = acc[j]; break;
-        case CL_ST0 + 1: CLOSYR_FORJ s1[j] = acc[j]; break;
-        case CL_ST0 + 2: CLOSYR_FORJ s2[j] = acc[j]; break;
-        case CL_ST0 + 3: CLOSYR_FORJ s3[j] = acc[j]; break;
-        case CL_ADDS0 + 0: CLOSYR_FORJ acc[j] = s0[j] + acc[j]; break;
-        case CL_ADDS0 + 1: CLOSYR_FORJ acc[j] = s1[j] + acc[j]; break;
-        case CL_ADDS0 + 2: CLOSYR_FORJ acc[j] = s2[j] + acc[j]; break;
-        case CL_ADDS0 + 3: CLOSYR_FORJ acc[j] = s3[j] + acc[j]; break;
-        case CL_MULS0 + 0: CLOSYR_FORJ acc[j] = s0[j] * acc[j]; break;
-        case CL_MULS0 + 1: CLOSYR_FORJ acc[j] = s1[j] * acc[j]; break;
-        case CL_MULS0 + 2: CLOSYR_FORJ acc[j] = s2[j] * acc[j]; break;
-        case CL_MULS0 + 3: CLOSYR_FORJ acc[j] = s3[j] * acc[j]; break;
         case CL_ST:
             if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ ls[a - CLOSYR_REG_SLOTS][j] = acc[j]; }
             else ev = (1u << P) - 1u;
