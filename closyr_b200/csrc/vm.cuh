@@ -16,6 +16,7 @@
 #include <cstdint>
 
 #include "../../include/closyr_b200.h"
+#include "vmath.cuh"
 
 namespace closyr {
 namespace dev {
@@ -62,10 +63,10 @@ __device__ __noinline__ double u_real(uint32_t op, double a, double c)
     case CL_RSQRT: return 1.0 / sqrt(a);
     case CL_POWI: return powi_real(a, (int)c);
     case CL_POWC: return pow(a, c);
-    case CL_EXP: return exp(a);
-    case CL_LOG: return log(a);
-    case CL_SIN: return sin(a);
-    case CL_COS: return cos(a);
+    case CL_EXP: { double t[1] = { a }; v_exp<1>(t); return t[0]; }
+    case CL_LOG: { double t[1] = { a }; v_log<1>(t); return t[0]; }
+    case CL_SIN:
+    case CL_COS: { double t[1] = { a }; v_sincos<1>(t, op == CL_COS ? 1 : 0); return t[0]; }
     case CL_TAN: return tan(a);
     case CL_ASIN: return asin(a);
     case CL_ACOS: return acos(a);
@@ -460,6 +461,45 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
 // ------------------------------------------------------------------------------------------------
 #define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
 
+// All elementary-function instructions of the fast path, 4 points per call (the struct travels in registers).
+// One copy of the 4-wide exp / log / sin / cos / reciprocal / square root; everything else falls back to four
+// scalar calls.  Returns the values and the mask of points that need the complete algebra (see below).
+struct D4 { double v[4]; };
+struct R4 { D4 d; uint32_t ev; };
+
+__device__ __noinline__ R4 k1_unary(uint32_t op, D4 in, double c)
+{
+    R4 out;
+    double a[4] = { in.v[0], in.v[1], in.v[2], in.v[3] };
+    switch (op) {
+    case CL_EXP: v_exp<4>(a); break;
+    case CL_LOG: v_log<4>(a); break;
+    case CL_SIN: v_sincos<4>(a, 0); break;
+    case CL_COS: v_sincos<4>(a, 1); break;
+    case CL_RECIP:
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = 1.0 / a[j];
+        break;
+    case CL_SQRT:
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = sqrt(a[j]);
+        break;
+    default:
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = u_real(op, a[j], c);
+        break;
+    }
+    uint32_t ev = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const double i_ = in.v[j];
+        if (is_inf(i_) || (a[j] != a[j] && i_ == i_)) ev |= 1u << j;
+        out.d.v[j] = a[j];
+    }
+    out.ev = ev;
+    return out;
+}
+
 // Loop-carried state is only the accumulator (P doubles); x is loaded once per chunk.  The spill slots live
 // in shared memory ([slot][point][lane], conflict-free): with slots in registers the compiler copied the whole
 // 40-register state at every dispatch (36 % of all issued instructions were IMAD.MOV, ncu profile r01_c).
@@ -517,12 +557,12 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
                 c = sconst[b];
                 if (nonfinite(c) || c == 0.0) { ev = (1u << P) - 1u; break; }
             }
-            CLOSYR_FORJ {
-                const double in_ = acc[j];
-                const double r_ = u_real(op, in_, c);
-                if (is_inf(in_) || (r_ != r_ && in_ == in_)) ev |= 1u << j;
-                acc[j] = r_;
-            }
+            static_assert(P == 4, "k1_unary is written for 4 points per lane");
+            D4 in;
+            CLOSYR_FORJ in.v[j] = acc[j];
+            const R4 r = k1_unary(op, in, c);
+            CLOSYR_FORJ acc[j] = r.d.v[j];
+            ev |= r.ev;
             break;
         }
         }
