@@ -76,31 +76,14 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     return s;
 }
 
-struct FullOut { double v0, v1, v2, v3; uint32_t nr; };
-
-// the complete algebra on the lane's 4 points, one at a time: one small copy of the code, small register footprint
-__device__ __noinline__ FullOut full_chunk(const uint32_t *scode, const double *sconst, double x0, double x1, double x2,
-                                           double x3)
-{
-    FullOut o;
-    o.nr = 0;
-    double v[4];
-    const double xs4[4] = { x0, x1, x2, x3 };
-#pragma unroll 1
-    for (int h = 0; h < 4; h++) {
-        const Z z = run_full(scode, sconst, xs4[h]);
-        const bool real = z.re == z.re && z.im == 0.0;
-        if (!real) o.nr |= 1u << h;
-        v[h] = real ? z.re : 0.0;
-    }
-    o.v0 = v[0]; o.v1 = v[1]; o.v2 = v[2]; o.v3 = v[3];
-    return o;
-}
-
 // evaluates one 128-point chunk: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points whose value is
-// not a real number (eval.clj:70-80 turns those into +Inf).  `mode` is the warp's adaptive state: 0 = try the
-// IEEE-real fast path first, 1 = go straight to the complete algebra (the previous chunk needed it).  Both
-// give bit-identical values wherever the fast path is valid, so the heuristic cannot change a score.
+// not a real number (eval.clj:70-80 turns those into +Inf).
+//
+// The IEEE-real fast path runs first; the points it reports are compacted across the warp (so 32 lanes work on
+// 32 reported points, whichever lanes they came from) and re-evaluated with the complete algebra, one point
+// per lane per round.  `mode` is the warp's adaptive state: when most points of the previous chunk needed the
+// complete algebra the fast pass is skipped.  Both evaluators give bit-identical values wherever the fast path
+// is valid, so the heuristic cannot change a score.
 __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool quirk, uint32_t quirk_off, int64_t base,
                                            int64_t n, const double *__restrict__ xs, double (&x)[4], double (&v)[4],
                                            uint32_t &valid, uint32_t &nr, uint32_t &mode)
@@ -126,20 +109,51 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
         for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
         return false;
     }
+    uint32_t ev = valid;
     if (mode == 0 && !is_const) {
-        uint32_t ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v);
-        ev &= valid;
+        ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v) & valid;
         // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
         nr &= valid;
-        if (!__any_sync(FULL, ev != 0)) return false;
     }
-    const FullOut o = full_chunk(st.scode, st.sconst, x[0], x[1], x[2], x[3]);
-    v[0] = o.v0; v[1] = o.v1; v[2] = o.v2; v[3] = o.v3;
-    nr = o.nr & valid;
-    mode = __any_sync(FULL, nr != 0) ? 1u : 0u;    // stay with the complete algebra while it keeps finding non-real points
+    const int lane = threadIdx.x & 31;
+    const uint32_t mine = __popc(ev);
+    uint32_t incl = mine;                                   // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return false;
+
+    // compact the reported points into the warp's slot area (free between two fast passes)
+    double *list = st.sslot - lane;                         // [128] x, then the result in place
+    uint32_t pos = incl - mine;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ((ev >> j) & 1u) list[pos++] = x[j];
+    __syncwarp();
+    for (uint32_t r = lane; r < total; r += 32) {
+        const Z z = run_full(st.scode, st.sconst, list[r]);
+        const bool real = z.re == z.re && z.im == 0.0;
+        list[r] = real ? z.re : __longlong_as_double(0x7ff8000000000000ll);    // NaN marks "not a real number"
+    }
+    __syncwarp();
+    pos = incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if ((ev >> j) & 1u) {
+            const double r = list[pos++];
+            if (r != r) { v[j] = 0.0; nr |= 1u << j; }
+            else { v[j] = r; nr &= ~(1u << j); }
+        }
+    }
+    __syncwarp();
+    mode = (total >= 96u) ? 1u : 0u;
     return true;
 }
 

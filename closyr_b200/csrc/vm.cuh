@@ -424,7 +424,7 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         const uint32_t w = scode[pc];
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
-        if (op == CL_END) return acc;
+        if (op == CL_END || acc.re != acc.re) return acc;     // Indeterminate absorbs every later instruction
         if (op <= CL_LDSPEC) {
             acc = op == CL_LDX ? zv(x, 0.0) : op == CL_LDC ? zv(sconst[b], 0.0)
                 : op == CL_LDZ ? zmk(sconst[b], sconst[b + 1]) : a == 0 ? zcinf() : zindet();
