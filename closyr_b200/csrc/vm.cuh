@@ -54,19 +54,26 @@ __device__ __forceinline__ double powi_real(double a, int n)
 
 enum { U_SINH = 100, U_COSH = 101 };
 
+// scalar entry points of the lean routines (vmath.cuh): a few hundred bytes each, shared by both evaluators
+__device__ __noinline__ double m_exp(double x) { double t[1] = { x }; v_exp<1>(t); return t[0]; }
+__device__ __noinline__ double m_log(double x) { double t[1] = { x }; v_log<1>(t); return t[0]; }
+__device__ __noinline__ double m_sincos(double x, int shift) { double t[1] = { x }; v_sincos<1>(t, shift); return t[0]; }
+__device__ __noinline__ double m_recip(double x) { return 1.0 / x; }
+__device__ __noinline__ double m_sqrt(double x) { return sqrt(x); }
+
 // real elementary function `op` of a (c = the literal operand of POWI / POWC)
 __device__ __noinline__ double u_real(uint32_t op, double a, double c)
 {
     switch (op) {
-    case CL_RECIP: return 1.0 / a;
-    case CL_SQRT: return sqrt(a);
-    case CL_RSQRT: return 1.0 / sqrt(a);
+    case CL_RECIP: return m_recip(a);
+    case CL_SQRT: return m_sqrt(a);
+    case CL_RSQRT: return m_recip(m_sqrt(a));
     case CL_POWI: return powi_real(a, (int)c);
     case CL_POWC: return pow(a, c);
-    case CL_EXP: { double t[1] = { a }; v_exp<1>(t); return t[0]; }
-    case CL_LOG: { double t[1] = { a }; v_log<1>(t); return t[0]; }
-    case CL_SIN:
-    case CL_COS: { double t[1] = { a }; v_sincos<1>(t, op == CL_COS ? 1 : 0); return t[0]; }
+    case CL_EXP: return m_exp(a);
+    case CL_LOG: return m_log(a);
+    case CL_SIN: return m_sincos(a, 0);
+    case CL_COS: return m_sincos(a, 1);
     case CL_TAN: return tan(a);
     case CL_ASIN: return asin(a);
     case CL_ACOS: return acos(a);
@@ -461,9 +468,8 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
 // ------------------------------------------------------------------------------------------------
 #define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
 
-// All elementary-function instructions of the fast path, 4 points per call (the struct travels in registers).
-// One copy of the 4-wide exp / log / sin / cos / reciprocal / square root; everything else falls back to four
-// scalar calls.  Returns the values and the mask of points that need the complete algebra (see below).
+// All elementary-function instructions of the fast path, 4 points per call (the struct travels in registers):
+// four calls of the scalar routine per instruction, one copy of every routine in the kernel image.  Returns the values and the mask of points that need the complete algebra (see below).
 struct D4 { double v[4]; };
 struct R4 { D4 d; uint32_t ev; };
 
@@ -471,24 +477,17 @@ __device__ __noinline__ R4 k1_unary(uint32_t op, D4 in, double c)
 {
     R4 out;
     double a[4] = { in.v[0], in.v[1], in.v[2], in.v[3] };
+#define CLOSYR_K4(expr) _Pragma("unroll") for (int j = 0; j < 4; j++) a[j] = (expr);
     switch (op) {
-    case CL_EXP: v_exp<4>(a); break;
-    case CL_LOG: v_log<4>(a); break;
-    case CL_SIN: v_sincos<4>(a, 0); break;
-    case CL_COS: v_sincos<4>(a, 1); break;
-    case CL_RECIP:
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[j] = 1.0 / a[j];
-        break;
-    case CL_SQRT:
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[j] = sqrt(a[j]);
-        break;
-    default:
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[j] = u_real(op, a[j], c);
-        break;
+    case CL_EXP: CLOSYR_K4(m_exp(a[j])) break;
+    case CL_LOG: CLOSYR_K4(m_log(a[j])) break;
+    case CL_SIN: CLOSYR_K4(m_sincos(a[j], 0)) break;
+    case CL_COS: CLOSYR_K4(m_sincos(a[j], 1)) break;
+    case CL_RECIP: CLOSYR_K4(m_recip(a[j])) break;
+    case CL_SQRT: CLOSYR_K4(m_sqrt(a[j])) break;
+    default: CLOSYR_K4(u_real(op, a[j], c)) break;
     }
+#undef CLOSYR_K4
     uint32_t ev = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
