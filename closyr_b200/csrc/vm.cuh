@@ -420,8 +420,18 @@ __device__ __noinline__ Z u_full(uint32_t op, Z a, double c)
     }
 }
 
-// One point through the program with the complete algebra.  Deliberately compact (one copy of everything,
-// slots in a small local array): it only runs for the 128-point chunks the fast path reported.
+// One point through the program with the complete algebra: only the points the fast path reported come
+// here.  Flat on purpose -- one switch, the real-line case of every instruction inline (the same IEEE sequence
+// as the fast path, through the same m_* routines), one call into z* only when a value is off the real line.
+// A first version went run_full -> u_full -> u_real -> m_*: 125 instructions per point-instruction and an
+// instruction-fetch stall at almost every step (ncu profile r01_f).
+#define CLOSYR_ZSET(expr) { acc = (expr); break; }
+#define CLOSYR_REAL1(cond, fast, zf)                        \
+    {                                                       \
+        const double x_ = acc.re;                           \
+        if (acc.im == 0.0 && (cond)) { acc.re = (fast); break; } \
+        CLOSYR_ZSET(zf(acc))                                \
+    }
 __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x)
 {
     Z slot[CLOSYR_MAX_SLOTS];
@@ -431,29 +441,61 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         const uint32_t w = scode[pc];
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
-        if (op == CL_END || acc.re != acc.re) return acc;     // Indeterminate absorbs every later instruction
-        if (op <= CL_LDSPEC) {
-            acc = op == CL_LDX ? zv(x, 0.0) : op == CL_LDC ? zv(sconst[b], 0.0)
-                : op == CL_LDZ ? zmk(sconst[b], sconst[b + 1]) : a == 0 ? zcinf() : zindet();
-        } else if (op <= CL_MULC) {
-            const double c = (op == CL_ADDX || op == CL_MULX) ? x : sconst[b];
-            if (acc.im == 0.0) acc.re = op <= CL_ADDC ? acc.re + c : acc.re * c;
-            else acc = op <= CL_ADDC ? zadd(acc, zv(c, 0.0)) : zmul(acc, zv(c, 0.0));
-        } else if (op < CL_ST) {
-            acc = u_full(op, acc, op == CL_POWC ? sconst[b] : (double)(short)b);
-        } else {
-            // slot instructions: a is the slot for both the generic and the register forms
-            const uint32_t kind = op >= CL_MULS0 ? CL_MULS : op >= CL_ADDS0 ? CL_ADDS : op >= CL_ST0 ? CL_ST : op;
-            if (kind == CL_ST) slot[a] = acc;
-            else {
-                const Z sl = slot[a];
-                if (kind == CL_POWS) acc = zpow(sl, acc);
-                else if (sl.im == 0.0 && acc.im == 0.0) acc.re = kind == CL_ADDS ? sl.re + acc.re : sl.re * acc.re;
-                else acc = kind == CL_ADDS ? zadd(sl, acc) : zmul(sl, acc);
+        if (acc.re != acc.re) return acc;                   // Indeterminate absorbs every later instruction
+        switch (op) {
+        case CL_END: return acc;
+        case CL_LDX: acc = zv(x, 0.0); break;
+        case CL_LDC: acc = zv(sconst[b], 0.0); break;
+        case CL_LDZ: acc = zmk(sconst[b], sconst[b + 1]); break;
+        case CL_LDSPEC: acc = a == 0 ? zcinf() : zindet(); break;
+        case CL_ADDX: if (acc.im == 0.0) { acc.re += x; break; } CLOSYR_ZSET(zadd(acc, zv(x, 0.0)))
+        case CL_ADDC: if (acc.im == 0.0) { acc.re += sconst[b]; break; } CLOSYR_ZSET(zadd(acc, zv(sconst[b], 0.0)))
+        case CL_MULX: if (acc.im == 0.0) { acc.re *= x; break; } CLOSYR_ZSET(zmul(acc, zv(x, 0.0)))
+        case CL_MULC: if (acc.im == 0.0) { acc.re *= sconst[b]; break; } CLOSYR_ZSET(zmul(acc, zv(sconst[b], 0.0)))
+        case CL_NEG: CLOSYR_REAL1(true, -x_, zneg)
+        case CL_SQR: if (acc.im == 0.0) { acc.re = acc.re * acc.re; break; } CLOSYR_ZSET(zmul(acc, acc))
+        case CL_RECIP: CLOSYR_REAL1(x_ != 0.0, m_recip(x_), zrecip)
+        case CL_SQRT: CLOSYR_REAL1(x_ >= 0.0, m_sqrt(x_), zsqrt)
+        case CL_RSQRT: if (acc.im == 0.0 && acc.re > 0.0) { acc.re = m_recip(m_sqrt(acc.re)); break; } CLOSYR_ZSET(zrecip(zsqrt(acc)))
+        case CL_POWI: {
+            const int n = (int)(short)b;
+            if (acc.im == 0.0) {
+                const double r = powi_real(acc.re, n < 0 ? -n : n);
+                if (n > 0) acc.re = r;
+                else if (r != 0.0) acc.re = m_recip(r);
+                else acc = zcinf();
+                break;
             }
+            CLOSYR_ZSET(zpowi(acc, n))
+        }
+        case CL_POWC: {
+            const double c = sconst[b];
+            if (acc.im == 0.0 && acc.re > 0.0 && !is_inf(acc.re) && !nonfinite(c) && c != 0.0) { acc.re = u_real(CL_POWC, acc.re, c); break; }
+            CLOSYR_ZSET(zpow(acc, zmk(c, 0.0)))
+        }
+        case CL_EXP: CLOSYR_REAL1(true, m_exp(x_), zexp)
+        case CL_LOG: CLOSYR_REAL1(x_ > 0.0, m_log(x_), zlog)
+        case CL_SIN: CLOSYR_REAL1(true, m_sincos(x_, 0), zsin)
+        case CL_COS: CLOSYR_REAL1(true, m_sincos(x_, 1), zcos)
+        case CL_TAN: CLOSYR_REAL1(true, u_real(CL_TAN, x_, 0.0), ztan)
+        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, u_real(CL_ASIN, x_, 0.0), zasin)
+        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, u_real(CL_ACOS, x_, 0.0), zacos)
+        case CL_ABS: CLOSYR_REAL1(true, fabs(x_), zabs)
+        default: {
+            // slot instructions: `a` is the slot for both the generic and the register forms
+            const uint32_t kind = op >= CL_MULS0 ? CL_MULS : op >= CL_ADDS0 ? CL_ADDS : op >= CL_ST0 ? CL_ST : op;
+            if (kind == CL_ST) { slot[a] = acc; break; }
+            const Z sl = slot[a];
+            if (kind == CL_POWS) acc = zpow(sl, acc);
+            else if (sl.im == 0.0 && acc.im == 0.0) acc.re = kind == CL_ADDS ? sl.re + acc.re : sl.re * acc.re;
+            else acc = kind == CL_ADDS ? zadd(sl, acc) : zmul(sl, acc);
+            break;
+        }
         }
     }
 }
+#undef CLOSYR_ZSET
+#undef CLOSYR_REAL1
 
 // ------------------------------------------------------------------------------------------------
 // fast path: P points per lane, IEEE real arithmetic, register-resident accumulator and slots 0..3.
