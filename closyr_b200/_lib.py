@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libclosyr_b200.so")
+SO_PATH = os.environ.get("CLOSYR_B200_LIB", os.path.join(_HERE, "libclosyr_b200.so"))   # override: A/B builds
 
 MIN_SCORE = -100000000.0      # reference src/closyr/ops.clj:24-26
 MAX_RESID = 1000000.0         # ops.clj:34-36

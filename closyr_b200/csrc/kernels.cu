@@ -157,7 +157,7 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
     return true;
 }
 
-__global__ void __launch_bounds__(SCORE_WARPS * 32, 4) score_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(SCORE_WARPS * 32, 8) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s_max[SCORE_WARPS];
