@@ -21,7 +21,7 @@ using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_LEVELS = 40;
-constexpr int SCORE_WARPS = 4;       // warps per CTA = warps sharing one staged program
+constexpr int MAX_SCORE_WARPS = 16;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -157,12 +157,12 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
     return true;
 }
 
-__global__ void __launch_bounds__(SCORE_WARPS * 32, 8) score_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 2) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_max[SCORE_WARPS];
-    __shared__ uint32_t s_nonreal[SCORE_WARPS], s_full[SCORE_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_max[MAX_SCORE_WARPS];
+    __shared__ uint32_t s_nonreal[MAX_SCORE_WARPS], s_full[MAX_SCORE_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t item = blockIdx.x;
     const int64_t e = item / p.n_tiles;
     const int tile = (int)(item - e * p.n_tiles);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32, 8) score_kernel(const ScoreP
         return;
     }
 
-    const Staged st = stage_program(p.pop, e, smem, tid, SCORE_WARPS * 32, p.chunks_per_tile);
+    const Staged st = stage_program(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile);
     __syncthreads();
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32, 8) score_kernel(const ScoreP
     double warp_mx = 0.0;
     uint32_t nonreal = 0, mode = 0;
     bool used_full = false;
-    for (int64_t c = c_lo + warp; c < c_hi; c += SCORE_WARPS) {
+    for (int64_t c = c_lo + warp; c < c_hi; c += nwarps) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4], y[4];
         uint32_t valid, nr;
@@ -243,8 +243,7 @@ __global__ void __launch_bounds__(SCORE_WARPS * 32, 8) score_kernel(const ScoreP
     const double tile_sum = cnt > 0 ? st.slvl[0] : 0.0;
     double tile_max = 0.0;
     uint32_t tile_nonreal = 0, tile_full = 0;
-#pragma unroll
-    for (int w = 0; w < SCORE_WARPS; w++) {
+    for (int w = 0; w < nwarps; w++) {
         tile_max = fmax(tile_max, s_max[w]);
         tile_nonreal += s_nonreal[w];
         tile_full |= s_full[w];
@@ -410,11 +409,19 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters)
 
 }  // namespace
 
+int score_warps(int32_t chunks_per_tile);
+
 void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
 {
     const int64_t items = p.pop.n_expr * p.n_tiles;
     if (items <= 0) return;
-    score_kernel<<<(unsigned)items, SCORE_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(p);
+    const int warps = score_warps(p.chunks_per_tile);
+    static size_t smem_opt_in = 0;
+    if (smem_bytes > 48 * 1024 && smem_bytes > smem_opt_in) {
+        cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        smem_opt_in = smem_bytes;
+    }
+    score_kernel<<<(unsigned)items, warps * 32, smem_bytes, (cudaStream_t)stream>>>(p);
 }
 
 void launch_finalize(const FinalizeParams &p, void *stream)
@@ -445,6 +452,11 @@ size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t ch
     return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 +
            ((size_t)max_code_words + 1) * 4 + 16;
 }
-int score_warps() { return SCORE_WARPS; }
+int score_warps(int32_t chunks_per_tile)
+{
+    int w = 1;
+    while (w < MAX_SCORE_WARPS && w < chunks_per_tile) w <<= 1;
+    return w;
+}
 
 }  // namespace closyr

@@ -61,7 +61,7 @@ void launch_eval(const EvalParams &p, size_t smem_bytes, void *stream);
 void launch_score_values(const double *f, const double *ys, int64_t n, int32_t leafs, double *out3, void *stream);
 void launch_fp64_probe(double *out, int iters, int blocks, void *stream);
 size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps);
-int score_warps();
+int score_warps(int32_t chunks_per_tile);
 constexpr int MAX_CHUNKS_PER_TILE = 1024;   // per-chunk sums of a tile live in shared memory (8 KiB)
 
 }  // namespace closyr
