@@ -166,7 +166,7 @@ int check_population(closyr_ctx *ctx, const closyr_population *pop)
 // tile size (in chunks, power of two) so that the launch has enough warps to fill the GPU
 int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
 {
-    const int64_t target_items = 148 * 2 * 6;          // CTAs of up to 16 warps, 2 resident per SM, a few waves
+    const int64_t target_items = 148 * 6;              // CTAs of up to 32 warps, 1 resident per SM, a few waves
     int64_t cpt = pow2_ceil(std::max<int64_t>(1, nchunks));
     while (cpt > MAX_CHUNKS_PER_TILE) cpt >>= 1;
     while (cpt > 4 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;

@@ -21,7 +21,7 @@ using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_LEVELS = 40;
-constexpr int MAX_SCORE_WARPS = 16;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
+constexpr int MAX_SCORE_WARPS = 32;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -157,7 +157,7 @@ __device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool
     return true;
 }
 
-__global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 2) score_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s_max[MAX_SCORE_WARPS];
