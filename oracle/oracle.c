@@ -708,6 +708,20 @@ int oracle_eval_raw(const char *expr, const double *xs, int64_t n, double *re, d
     return 0;
 }
 
+/* (sum, max) of the residuals of chunks [chunk_begin, chunk_end) in the CUDA path's reduction shape; the range
+ * must be an index-aligned power-of-two span of 128-point chunks (or its tail): one rank's share under point sharding */
+void oracle_tree_partial(const double *resid, int64_t n, int64_t chunk_begin, int64_t chunk_end, double *sum, double *mx)
+{
+    int64_t span = 1;
+    while (span < chunk_end - chunk_begin) span <<= 1;
+    double s = chunk_begin < chunk_end ? tree_sum(resid, n, chunk_begin, span) : -1.0;
+    double m = 0.0;
+    int64_t hi = chunk_end * 128 < n ? chunk_end * 128 : n;
+    for (int64_t i = chunk_begin * 128; i < hi; i++) if (resid[i] > m) m = resid[i];
+    *sum = s < 0.0 ? 0.0 : s;
+    *mx = m;
+}
+
 double oracle_compute_residual(double expected, double actual) { return compute_residual(expected, actual); }
 
 double oracle_score_from_f(const double *f, const double *ys, int64_t n, int leafs, int sum_mode)

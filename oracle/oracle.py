@@ -51,6 +51,8 @@ def lib():
                                          C.c_int, dp]
         L.oracle_score_batch.restype = C.c_int
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_tree_partial.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, dp, dp]
+        L.oracle_tree_partial.restype = None
         L.oracle_set_jitter.argtypes = [C.c_int]
         L.oracle_set_jitter.restype = None
         _lib = L
@@ -96,6 +98,14 @@ def eval_raw(expr, xs):
 
 def compute_residual(expected, actual):
     return lib().oracle_compute_residual(float(expected), float(actual))
+
+
+def tree_partial(resid, chunk_begin, chunk_end):
+    """(sum, max) of residual chunks [chunk_begin, chunk_end) in the CUDA reduction shape (aligned power-of-two span)."""
+    r, pr = _d(resid)
+    s, m = C.c_double(), C.c_double()
+    lib().oracle_tree_partial(pr, len(r), chunk_begin, chunk_end, C.byref(s), C.byref(m))
+    return s.value, m.value
 
 
 def score_from_f(f, ys, leafs, sum_mode=SUM_LEFT_FOLD):
