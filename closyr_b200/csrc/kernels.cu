@@ -416,11 +416,9 @@ void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
     const int64_t items = p.pop.n_expr * p.n_tiles;
     if (items <= 0) return;
     const int warps = score_warps(p.chunks_per_tile);
-    static size_t smem_opt_in = 0;
-    if (smem_bytes > 48 * 1024 && smem_bytes > smem_opt_in) {
+    // opt in to > 48 KiB of dynamic shared memory; the attribute is per device, so it is set at every launch
+    if (smem_bytes > 48 * 1024)
         cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        smem_opt_in = smem_bytes;
-    }
     score_kernel<<<(unsigned)items, warps * 32, smem_bytes, (cudaStream_t)stream>>>(p);
 }
 
