@@ -76,85 +76,98 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     return s;
 }
 
-// evaluates one 128-point chunk: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points whose value is
-// not a real number (eval.clj:70-80 turns those into +Inf).
+// One round of a CTA = one 128-point chunk per warp: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points
+// whose value is not a real number (eval.clj:70-80 turns those into +Inf).
 //
-// The IEEE-real fast path runs first; the points it reports are compacted across the warp (so 32 lanes work on
-// 32 reported points, whichever lanes they came from) and re-evaluated with the complete algebra, one point
-// per lane per round.  `mode` is the warp's adaptive state: when most points of the previous chunk needed the
-// complete algebra the fast pass is skipped.  Both evaluators give bit-identical values wherever the fast path
-// is valid, so the heuristic cannot change a score.
-__device__ __forceinline__ bool eval_chunk(const Staged &st, bool is_const, bool quirk, uint32_t quirk_off, int64_t base,
-                                           int64_t n, const double *__restrict__ xs, double (&x)[4], double (&v)[4],
-                                           uint32_t &valid, uint32_t &nr, uint32_t &mode)
+// Every warp first runs the IEEE-real fast path on its chunk.  The points it reports are compacted across
+// the WHOLE CTA into one list and re-evaluated with the complete algebra by all threads, one point per thread
+// per pass -- so the extra work of a chunk that left the real line is shared by the 32 warps instead of
+// stalling the CTA behind one warp.  `mode` is the CTA's adaptive state: when most points of the previous
+// round needed the complete algebra the fast pass is skipped.  Both evaluators give bit-identical values
+// wherever the fast path is valid, so the heuristic cannot change a score.
+// Must be called by every thread of the CTA (it contains __syncthreads).
+struct Round {
+    double *list;          // [warps * 128] reported x values, replaced in place by their results
+    uint32_t *counts;      // [2][32] reported points per warp, double-buffered by round parity
+};
+
+__device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bool active, bool is_const, bool quirk,
+                                           uint32_t quirk_off, int64_t base, int64_t n, const double *__restrict__ xs,
+                                           double (&x)[4], double (&v)[4], uint32_t &valid, uint32_t &nr, uint32_t &mode,
+                                           uint32_t round_parity)
 {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     valid = 0;
     nr = 0;
-    if (base + 3 < n) {
-        const double2 a = *reinterpret_cast<const double2 *>(xs + base);
-        const double2 b = *reinterpret_cast<const double2 *>(xs + base + 2);
-        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
-        valid = 0xfu;
-    } else {
+    uint32_t ev = 0;
+    if (active) {
+        if (base + 3 < n) {
+            const double2 a = *reinterpret_cast<const double2 *>(xs + base);
+            const double2 b = *reinterpret_cast<const double2 *>(xs + base + 2);
+            x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+            valid = 0xfu;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const bool ok = base + j < n;
-            x[j] = ok ? xs[base + j] : 1.0;
-            valid |= (ok ? 1u : 0u) << j;
+            for (int j = 0; j < 4; j++) {
+                const bool ok = base + j < n;
+                x[j] = ok ? xs[base + j] : 1.0;
+                valid |= (ok ? 1u : 0u) << j;
+            }
         }
-    }
-    if (quirk) {
-        // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
+        if (quirk) {
+            // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
-        return false;
-    }
-    uint32_t ev = valid;
-    if (mode == 0 && !is_const) {
-        ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v) & valid;
-        // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
+            for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
+        } else if (mode == 0 && !is_const) {
+            ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v) & valid;
+            // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
-        nr &= valid;
+            for (int j = 0; j < 4; j++)
+                if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
+            nr &= valid;
+        } else ev = valid;
     }
-    const int lane = threadIdx.x & 31;
+    // CTA-wide compaction of the reported points
     const uint32_t mine = __popc(ev);
-    uint32_t incl = mine;                                   // inclusive prefix sum over the lanes
+    uint32_t incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += t;
     }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint32_t *cnt = rd.counts + round_parity * 32;
+    if (lane == 31) cnt[warp] = incl;
+    __syncthreads();
+    uint32_t cw = lane < nwarps ? cnt[lane] : 0u, ci = cw;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, ci, d);
+        if (lane >= d) ci += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, ci, 31);
     if (total == 0) return false;
-
-    // compact the reported points into the warp's slot area (free between two fast passes)
-    double *list = st.sslot - lane;                         // [128] x, then the result in place
-    uint32_t pos = incl - mine;
-    __syncwarp();
+    uint32_t pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if ((ev >> j) & 1u) list[pos++] = x[j];
-    __syncwarp();
-    for (uint32_t r = lane; r < total; r += 32) {
-        const Z z = run_full(st.scode, st.sconst, list[r]);
+        if ((ev >> j) & 1u) rd.list[pos++] = x[j];
+    __syncthreads();
+    for (uint32_t r = tid; r < total; r += blockDim.x) {
+        const Z z = run_full(st.scode, st.sconst, rd.list[r]);
         const bool real = z.re == z.re && z.im == 0.0;
-        list[r] = real ? z.re : __longlong_as_double(0x7ff8000000000000ll);    // NaN marks "not a real number"
+        rd.list[r] = real ? z.re : __longlong_as_double(0x7ff8000000000000ll);    // NaN marks "not a real number"
     }
-    __syncwarp();
-    pos = incl - mine;
+    __syncthreads();
+    pos -= mine;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if ((ev >> j) & 1u) {
-            const double r = list[pos++];
+            const double r = rd.list[pos++];
             if (r != r) { v[j] = 0.0; nr |= 1u << j; }
             else { v[j] = r; nr &= ~(1u << j); }
         }
     }
-    __syncwarp();
-    mode = (total >= 96u) ? 1u : 0u;
-    return true;
+    mode = (total * 4u >= (uint32_t)blockDim.x * 4u * 3u) ? 1u : 0u;      // >= 75 % of the round's points
+    return mine != 0;
 }
 
 __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         return;
     }
 
-    const Staged st = stage_program(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile);
+    const Staged st = stage_program(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS);
     __syncthreads();
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
@@ -197,14 +210,19 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     if (c_hi > p.chunk_end) c_hi = p.chunk_end;
     const int cnt = (int)(c_hi - c_lo);
 
+    __shared__ uint32_t s_counts[64];
+    const Round rd = { st.slvl + p.chunks_per_tile, s_counts };
     double warp_mx = 0.0;
-    uint32_t nonreal = 0, mode = 0;
+    uint32_t nonreal = 0, mode = 0, parity = 0;
     bool used_full = false;
-    for (int64_t c = c_lo + warp; c < c_hi; c += nwarps) {
+    for (int64_t c0 = c_lo; c0 < c_hi; c0 += nwarps, parity ^= 1u) {
+        const int64_t c = c0 + warp;
+        const bool active = c < c_hi;
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4], y[4];
         uint32_t valid, nr;
-        used_full |= eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode);
+        used_full |= eval_round(st, rd, active, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode, parity);
+        if (!active) continue;
         if (base + 3 < p.n) {
             const double2 a = *reinterpret_cast<const double2 *>(p.ys + base);
             const double2 b = *reinterpret_cast<const double2 *>(p.ys + base + 2);
@@ -326,20 +344,22 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
         if (lane == 0) p.status[e] = 1;
         return;
     }
-    const Staged st = stage_program(p.pop, e, smem, lane, 32, 0);
+    const Staged st = stage_program(p.pop, e, smem, lane, 32, CHUNK_POINTS);
     __syncwarp();
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
     const uint32_t quirk_off = aux & 0xffffu;
     const int64_t nchunks = (p.n + CHUNK_POINTS - 1) / CHUNK_POINTS;
+    __shared__ uint32_t s_counts[64];
+    const Round rd = { st.slvl, s_counts };
     uint32_t nonreal = 0, mode = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t c = 0; c < nchunks; c++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         double x[4], v[4];
         uint32_t valid, nr;
-        eval_chunk(st, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode);
+        eval_round(st, rd, true, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode, (uint32_t)(c & 1));
         nonreal += __popc(nr);
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -448,6 +468,7 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
 size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps)
 {
     return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 +
+           (size_t)warps * CHUNK_POINTS * 8 +
            ((size_t)max_code_words + 1) * 4 + 16;
 }
 int score_warps(int32_t chunks_per_tile)
