@@ -1,7 +1,7 @@
 // kernels.cu -- sm_100a kernels of the scoring path.
 //
-// score_kernel: one CTA of SCORE_WARPS warps per (expression, tile of points).  The program and its constant
-// pool are staged once in shared memory and every warp of the CTA interprets it on different 128-point chunks
+// score_kernel: one CTA of up to 32 warps per (expression, tile of points).  The program and its constant
+// pool are staged once in shared memory (two TMA bulk copies, cp.async.bulk + mbarrier) and every warp of the CTA interprets it on different 128-point chunks
 // (so the warps of a CTA fetch the same instructions at about the same time: 4x fewer distinct instruction
 // streams per SM than one program per warp).  Lanes stride over the points, 4 consecutive points per lane per
 // pass (two 16-byte loads of xs and of ys per lane, a warp reads 1 KiB contiguous); the residuals are reduced
@@ -170,6 +170,60 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
     return mine != 0;
 }
 
+// ---- TMA bulk staging (cp.async.bulk + mbarrier): the population buffer is laid out for it (every program and
+// every constant pool starts on a 16-byte boundary and is a multiple of 16 bytes long)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// stages one program with two TMA bulk copies ([warp slots | constants | scratch | code]); every thread of the
+// CTA calls it, thread 0 issues the copies and everybody waits on the mbarrier (single use: parity 0)
+__device__ __forceinline__ Staged stage_program_tma(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
+                                                    int nthreads, int nlvl, unsigned long long *bar)
+{
+    const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
+    const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
+    const uint32_t ncode = c1 - c0, nk = k1 - k0;
+    double *sslot = reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31);
+    double *sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
+    double *slvl = sconst + nk;
+    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + ((nlvl + 1) & ~1));      // 16-byte aligned
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, ncode * 4u + nk * 8u);
+        if (nk) bulk_g2s(sconst, pop.consts + (k0 - pop.const_base), nk * 8u, bar);
+        bulk_g2s(scode, pop.code + (c0 - pop.code_base), ncode * 4u, bar);
+    }
+    __syncthreads();                 // the initialised barrier is visible to every waiter
+    mbar_wait(bar, 0);
+    Staged s = { scode, sconst, slvl, sslot };
+    return s;
+}
+
 __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -198,8 +252,8 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         return;
     }
 
-    const Staged st = stage_program(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS);
-    __syncthreads();
+    __shared__ __align__(8) unsigned long long s_bar;
+    const Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS, &s_bar);
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -467,7 +521,7 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
 
 size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps)
 {
-    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)chunks_per_tile * 8 +
+    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)((chunks_per_tile + 1) & ~1) * 8 +
            (size_t)warps * CHUNK_POINTS * 8 +
            ((size_t)max_code_words + 1) * 4 + 16;
 }
