@@ -157,6 +157,31 @@ __device__ __noinline__ Z zmul(Z a, Z b)
     return zmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
 }
 
+// add / multiply of finite operands with finite results: the arithmetic of zadd / zmul without the tag plumbing
+// (the complete-algebra interpreter spends most of its instructions on + and * of ordinary complex numbers)
+__device__ __forceinline__ bool zfinite(Z a) { return !(nonfinite(a.re) || nonfinite(a.im)); }
+__device__ __forceinline__ Z zchop(Z r)
+{
+    if (r.im != 0.0 && fabs(r.im) <= CLOSYR_CHOP_REL * fabs(r.re)) r.im = 0.0;
+    else if (r.re != 0.0 && fabs(r.re) <= CLOSYR_CHOP_REL * fabs(r.im)) r.re = 0.0;
+    return r;
+}
+__device__ __forceinline__ Z lean_add(Z a, Z b)
+{
+    const Z r = zv(a.re + b.re, a.im + b.im);
+    if (zfinite(a) && zfinite(b) && zfinite(r)) return zchop(r);
+    return zadd(a, b);
+}
+__device__ __forceinline__ Z lean_mul(Z a, Z b)         // at least one operand is off the real line
+{
+    Z r;
+    if (a.im == 0.0) r = zv(a.re * b.re, a.re * b.im);
+    else if (b.im == 0.0) r = zv(a.re * b.re, a.im * b.re);
+    else r = zv(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+    if (zfinite(a) && zfinite(b) && zfinite(r)) return zchop(r);
+    return zmul(a, b);
+}
+
 __device__ __forceinline__ Z zneg(Z a)
 {
     int t = ztag(a);
@@ -448,12 +473,12 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         case CL_LDC: acc = zv(sconst[b], 0.0); break;
         case CL_LDZ: acc = zmk(sconst[b], sconst[b + 1]); break;
         case CL_LDSPEC: acc = a == 0 ? zcinf() : zindet(); break;
-        case CL_ADDX: if (acc.im == 0.0) { acc.re += x; break; } CLOSYR_ZSET(zadd(acc, zv(x, 0.0)))
-        case CL_ADDC: if (acc.im == 0.0) { acc.re += sconst[b]; break; } CLOSYR_ZSET(zadd(acc, zv(sconst[b], 0.0)))
-        case CL_MULX: if (acc.im == 0.0) { acc.re *= x; break; } CLOSYR_ZSET(zmul(acc, zv(x, 0.0)))
-        case CL_MULC: if (acc.im == 0.0) { acc.re *= sconst[b]; break; } CLOSYR_ZSET(zmul(acc, zv(sconst[b], 0.0)))
+        case CL_ADDX: if (acc.im == 0.0) { acc.re += x; break; } CLOSYR_ZSET(lean_add(acc, zv(x, 0.0)))
+        case CL_ADDC: if (acc.im == 0.0) { acc.re += sconst[b]; break; } CLOSYR_ZSET(lean_add(acc, zv(sconst[b], 0.0)))
+        case CL_MULX: if (acc.im == 0.0) { acc.re *= x; break; } CLOSYR_ZSET(lean_mul(acc, zv(x, 0.0)))
+        case CL_MULC: if (acc.im == 0.0) { acc.re *= sconst[b]; break; } CLOSYR_ZSET(lean_mul(acc, zv(sconst[b], 0.0)))
         case CL_NEG: CLOSYR_REAL1(true, -x_, zneg)
-        case CL_SQR: if (acc.im == 0.0) { acc.re = acc.re * acc.re; break; } CLOSYR_ZSET(zmul(acc, acc))
+        case CL_SQR: if (acc.im == 0.0) { acc.re = acc.re * acc.re; break; } CLOSYR_ZSET(lean_mul(acc, acc))
         case CL_RECIP: CLOSYR_REAL1(x_ != 0.0, m_recip(x_), zrecip)
         case CL_SQRT: CLOSYR_REAL1(x_ >= 0.0, m_sqrt(x_), zsqrt)
         case CL_RSQRT: if (acc.im == 0.0 && acc.re > 0.0) { acc.re = m_recip(m_sqrt(acc.re)); break; } CLOSYR_ZSET(zrecip(zsqrt(acc)))
@@ -488,7 +513,7 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
             const Z sl = slot[a];
             if (kind == CL_POWS) acc = zpow(sl, acc);
             else if (sl.im == 0.0 && acc.im == 0.0) acc.re = kind == CL_ADDS ? sl.re + acc.re : sl.re * acc.re;
-            else acc = kind == CL_ADDS ? zadd(sl, acc) : zmul(sl, acc);
+            else acc = kind == CL_ADDS ? lean_add(sl, acc) : lean_mul(sl, acc);
             break;
         }
         }
