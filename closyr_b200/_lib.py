@@ -52,7 +52,25 @@ EXPORTS = [
     "closyr_builder_create", "closyr_builder_destroy", "closyr_builder_clear", "closyr_builder_add",
     "closyr_builder_add_many", "closyr_builder_view", "closyr_to_fullform", "closyr_leaf_count", "closyr_free",
     "closyr_generate_population",
+    "closyr_jrandom_rand_ints", "closyr_jrandom_shuffle", "closyr_mutation_count", "closyr_mutation_info",
+    "closyr_mutate_expr", "closyr_crossover_expr", "closyr_ga_create", "closyr_ga_destroy",
+    "closyr_ga_population_count", "closyr_ga_set_expr", "closyr_ga_pending", "closyr_ga_pending_indices",
+    "closyr_ga_commit_scores", "closyr_ga_evolve", "closyr_ga_best", "closyr_ga_expr",
 ]
+
+
+class GAStats(C.Structure):
+    """closyr_ga_stats"""
+    _fields_ = [
+        ("n_pop", C.c_int64),
+        ("n_children", C.c_int64),
+        ("n_mutation_children", C.c_int64),
+        ("n_crossover_children", C.c_int64),
+        ("max_pair_sum", C.c_double),
+        ("early_stop", C.c_int32),
+        ("reserved", C.c_int32),
+        ("ms_modify", C.c_double),
+    ]
 
 _lib = None
 
@@ -105,6 +123,22 @@ def lib():
         "closyr_leaf_count": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
         "closyr_free": (None, [vp]),
         "closyr_generate_population": (C.c_int, [vp, u64, i64, i32, i32, C.POINTER(vp)]),
+        "closyr_jrandom_rand_ints": (C.c_int, [i64, i64, i32, C.POINTER(i32)]),
+        "closyr_jrandom_shuffle": (C.c_int, [i64, i32, C.POINTER(i32)]),
+        "closyr_mutation_count": (i32, []),
+        "closyr_mutation_info": (C.c_int, [i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+        "closyr_mutate_expr": (C.c_int, [C.c_char_p, i32, i32, i64, C.POINTER(vp)]),
+        "closyr_crossover_expr": (C.c_int, [C.c_char_p, C.c_char_p, i32, i64, C.POINTER(vp)]),
+        "closyr_ga_create": (C.c_int, [i64, i32, i64, i32, C.POINTER(vp)]),
+        "closyr_ga_destroy": (None, [vp]),
+        "closyr_ga_population_count": (i64, [vp]),
+        "closyr_ga_set_expr": (C.c_int, [vp, i64, C.c_char_p]),
+        "closyr_ga_pending": (C.c_int, [vp, popp, C.POINTER(i64)]),
+        "closyr_ga_pending_indices": (C.c_int, [vp, C.POINTER(i64), i64]),
+        "closyr_ga_commit_scores": (C.c_int, [vp, dp, i64]),
+        "closyr_ga_evolve": (C.c_int, [vp, C.POINTER(GAStats)]),
+        "closyr_ga_best": (C.c_int, [vp, C.POINTER(i64), dp, C.POINTER(i32), C.POINTER(vp)]),
+        "closyr_ga_expr": (C.c_int, [vp, i64, C.POINTER(vp), dp, C.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -606,6 +606,28 @@ NodeP parse_expr(const char *text, std::string *err)
     return n;
 }
 
+NodeP canon_plus(std::vector<NodeP> terms) { return c_plus(std::move(terms)); }
+NodeP canon_times(std::vector<NodeP> factors) { return c_times(std::move(factors)); }
+NodeP canon_power(NodeP base, NodeP exponent) { return c_power(std::move(base), std::move(exponent)); }
+NodeP canon_neg(NodeP a) { return c_neg(std::move(a)); }
+
+bool same_expr(const Node &a, const Node &b)
+{
+    if (a.kind != b.kind || a.args.size() != b.args.size()) return false;
+    switch (a.kind) {
+    case Kind::Int: if (a.big != b.big || (a.big ? a.name != b.name : a.num != b.num)) return false; break;
+    case Kind::Rat: if (a.num != b.num || a.den != b.den) return false; break;
+    case Kind::Real: if (memcmp(&a.val, &b.val, sizeof(double)) != 0) return false; break;
+    case Kind::Complex: if (a.val != b.val || a.val2 != b.val2) return false; break;
+    case Kind::DInf: if (a.val != b.val) return false; break;
+    case Kind::Unknown: if (a.name != b.name) return false; break;
+    default: break;
+    }
+    for (size_t i = 0; i < a.args.size(); i++)
+        if (!same_expr(*a.args[i], *b.args[i])) return false;
+    return true;
+}
+
 std::string to_fullform(const Node &n)
 {
     std::string s;

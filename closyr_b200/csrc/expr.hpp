@@ -62,4 +62,13 @@ NodeP parse_expr(const char *text, std::string *err);
 
 std::string to_fullform(const Node &n);
 
+// Canonicalising constructors: what `.eval` in `->phenotype` (common.clj:135-146) does to the shapes the GA
+// operators build -- flattening, exact rational folding, x^a*x^b, (u^a)^k, -1*(a+b).  The infix parser uses them.
+NodeP canon_plus(std::vector<NodeP> terms);
+NodeP canon_times(std::vector<NodeP> factors);
+NodeP canon_power(NodeP base, NodeP exponent);
+NodeP canon_neg(NodeP a);
+// structural equality (same tree, same literals)
+bool same_expr(const Node &a, const Node &b);
+
 }  // namespace closyr

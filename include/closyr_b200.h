@@ -223,6 +223,57 @@ void closyr_free(void *p);
 int closyr_generate_population(closyr_builder *b, uint64_t seed, int64_t n_expr, int32_t max_leafs, int32_t mix,
                                char **out_texts);
 
+/*
+ * Stand-alone GA driver: the host loop around the scorer for runs without a
+ * JVM.  Replaces, for measurement purposes, ga/evolve (src/closyr/ga.clj:58-88), ops/mutation-fn and
+ * ops/crossover-fn (src/closyr/ops.clj:143-188), ops.modify (src/closyr/ops/modify.clj:77-288) with the 96
+ * operators of src/closyr/ops/initialize.clj:35-665, and the generator of src/closyr/util/prng.clj:16-59.
+ * The scorer stays outside, as the `score-fn` closure does in ga/initialize (ga.clj:11-17):
+ *     closyr_ga_pending -> closyr_score_batch (or any scorer) -> closyr_ga_commit_scores -> closyr_ga_evolve -> ...
+ * No GPU is needed for anything in this block.
+ */
+typedef struct closyr_ga closyr_ga;
+
+typedef struct closyr_ga_stats {
+    int64_t n_pop;
+    int64_t n_children;             /* phenotypes created by this evolve (they are the next pending batch) */
+    int64_t n_mutation_children;
+    int64_t n_crossover_children;
+    double max_pair_sum;            /* max over pairs of e1-score + e2-score (ga.clj:46, :pop-scores) */
+    int32_t early_stop;             /* any pair sum > -1e-3 (symbolic_regression.clj:409-414) */
+    int32_t reserved;
+    double ms_modify;               /* host time spent in shuffle + compete */
+} closyr_ga_stats;
+
+/* java.util.Random restated (golden pairs: test/closyr/util_prng_test.clj:22-25): count values of rand-int(n) */
+int closyr_jrandom_rand_ints(int64_t seed, int64_t n, int32_t count, int32_t *out);
+/* Collections.shuffle of 0..n-1 with a fresh generator (prng.clj:49-55) */
+int closyr_jrandom_shuffle(int64_t seed, int32_t n, int32_t *perm);
+
+/* the mutation table, in the order of initialize.clj */
+int32_t closyr_mutation_count(void);
+int closyr_mutation_info(int32_t index, const char **op, const char **label);
+/* apply one operator to an expression; use_rng 0 = every should-modify draw says yes (rand stubbed to 0.0 as in
+ * test/closyr/ops_modify_test.clj:754-756).  *out is malloc'd FullForm text (closyr_free). */
+int closyr_mutate_expr(const char *expr_text, int32_t index, int32_t use_rng, int64_t seed, char **out);
+int closyr_crossover_expr(const char *expr1, const char *expr2, int32_t max_leafs, int64_t seed, char **out);
+
+/* population of pop_count phenotypes `x` (initialize.clj:17-33); threads <= 0: all host cores; threads == 1
+ * keeps a single generator stream for the whole run */
+int closyr_ga_create(int64_t pop_count, int32_t max_leafs, int64_t seed, int32_t threads, closyr_ga **out);
+void closyr_ga_destroy(closyr_ga *ga);
+int64_t closyr_ga_population_count(closyr_ga *ga);
+int closyr_ga_set_expr(closyr_ga *ga, int64_t index, const char *expr_text);
+/* the phenotypes without a score, compiled into a population (valid until the next closyr_ga_* call) */
+int closyr_ga_pending(closyr_ga *ga, closyr_population *view, int64_t *n_pending);
+int closyr_ga_pending_indices(closyr_ga *ga, int64_t *out, int64_t capacity);
+int closyr_ga_commit_scores(closyr_ga *ga, const double *scores, int64_t n);
+/* one ga/evolve on a fully scored population: shuffle, compete in pairs, create the children */
+int closyr_ga_evolve(closyr_ga *ga, closyr_ga_stats *stats);
+/* ops/sort-population's first element (ops.clj:191-201) */
+int closyr_ga_best(closyr_ga *ga, int64_t *index, double *score, int32_t *leafs, char **expr_fullform);
+int closyr_ga_expr(closyr_ga *ga, int64_t index, char **expr_fullform, double *score, int32_t *scored);
+
 #ifdef __cplusplus
 }
 #endif
