@@ -48,7 +48,7 @@ def main():
         ctx.set_points(xs, ys)
         ga = G.GA(G.gpu_scorer(ctx, cfg["max_leafs"]), cfg["pop"], cfg["max_leafs"], seed=888, threads=0)
         ga.score_pending()                              # generation 0: the whole population
-        launches0 = ctx.kernel_launch_count()
+        launches0 = ctx.kernel_launches
         per_gen = []
         t_all = time.perf_counter()
         done = 0
@@ -61,7 +61,7 @@ def main():
             if early and st["early_stop"]:
                 break
         total_ms = (time.perf_counter() - t_all) * 1e3
-        launches = ctx.kernel_launch_count() - launches0
+        launches = ctx.kernel_launches - launches0
         score, leafs, expr = ga.best()
     t = ga.timing
     print(json.dumps({

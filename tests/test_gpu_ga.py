@@ -35,11 +35,11 @@ def test_readme_run_on_gpu():       # configs[0]: pop 25, 5 iterations, xs 0..6,
     ys = np.array([1, 2, 30, 4, 5, 6, 10], dtype=np.float64)
     with cb.Context([0]) as ctx:
         ctx.set_points(xs, ys)
-        before = ctx.kernel_launch_count()
+        before = ctx.kernel_launches
         ga = G.GA(G.gpu_scorer(ctx, 40), 25, 40, seed=888, threads=1)
         best = []
         done = ga.run(5, on_iteration=lambda i, st, g: best.append(g.best()[0]))
-        assert ctx.kernel_launch_count() > before          # the scores came from the kernels
+        assert ctx.kernel_launches > before          # the scores came from the kernels
     assert done == 5 and len(ga) == 25
     assert all(b1 >= b0 for b0, b1 in zip(best, best[1:]))
     assert best[-1] > -38.57143242857143
