@@ -186,7 +186,14 @@ def main():
     ap.add_argument("--shard", default="population", choices=["population", "points"])
     ap.add_argument("--cpu-sample", type=int, default=20000, help="expressions scored by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--population", type=int, default=0, help="override the workload's population (configs[4] sweep)")
+    ap.add_argument("--points", type=int, default=0, help="override the workload's point count (configs[4] sweep)")
     args = ap.parse_args()
+    if args.population or args.points:
+        p0, n0, ml, mx, d0 = WORKLOADS[args.workload]
+        p1, n1 = args.population or p0, args.points or n0
+        WORKLOADS[args.workload] = (p1, n1, ml, mx, "configs[4] sweep point (%s shape): pop %d x %d points, max-leafs %d"
+                                    % (args.workload, p1, n1, ml))
     if args.impl == "reference":
         run_reference(args)
         return
