@@ -71,7 +71,11 @@ def algorithmic_work(arrays):
         bits = np.floor(np.log2(np.maximum(a, 1))).astype(np.int64)
         pop = np.array([bin(int(v)).count("1") for v in a], dtype=np.int64)
         slots[powi] = bits + pop - 1 + np.where(n < 0, 5, 0)
-    insn = (op != 0).astype(np.int64)
+    # node evaluations: one per instruction plus one per fused leaf load / slot store (ISA v1.1 modifiers), so
+    # the count means the same as it did for v1 programs
+    a = (code >> 8) & 0xFF
+    mod = ((op == 1) | (op == 2) | ((op >= 9) & (op <= 23)))
+    insn = (op != 0).astype(np.int64) + (mod & ((a & 2) != 0)) + (mod & (op >= 9) & ((a & 1) != 0))
     off = arrays["code_off"].astype(np.int64)
     starts = off[:-1]
     per_slots = np.add.reduceat(slots, starts) if len(starts) else np.zeros(0, np.int64)

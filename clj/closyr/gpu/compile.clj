@@ -1,6 +1,6 @@
 (ns closyr.gpu.compile
   "Lowers a canonical Symja IExpr (what `ops-common/->phenotype` holds, src/closyr/ops/common.clj:135-146)
-   to the postfix bytecode of include/closyr_b200.h (ISA v1).
+   to the postfix bytecode of include/closyr_b200.h (ISA v1.1).
 
    This is the Clojure mirror of closyr_b200/csrc/compiler.cpp.  It MUST emit the same instruction words,
    the same constant pool (first-use order, de-duplicated by bit pattern) and the same meta/aux words for
@@ -91,8 +91,26 @@
 (defn- emitter []
   {:code (ArrayList.) :consts (ArrayList.) :overflow (volatile! false) :max-slot (volatile! -1)})
 
-(defn- emit! [{:keys [^ArrayList code overflow]} op a b]
-  (if (> (+ (.size code) 8) MAX-CODE) (vreset! overflow true) (.add code (insn op a b))))
+(def ^:const M-SRCX 1) (def ^:const M-PUSH 2)
+
+(defn- emit!
+  "Appends one instruction, applying the ISA v1.1 fusions exactly as Emitter::emit in compiler.cpp does:
+   `ST0+k ; LDX|LDC` becomes the load with M-PUSH and slot k, `LDX ; f` becomes f with M-SRCX."
+  [{:keys [^ArrayList code overflow]} op a b]
+  (if (> (+ (.size code) 8) MAX-CODE)
+    (vreset! overflow true)
+    (let [n    (.size code)
+          last (if (pos? n) (long (.get code (dec n))) 0)
+          lop  (bit-and last 0xff)
+          la   (bit-and (bit-shift-right last 8) 0xff)]
+      (cond
+        (and (pos? n) (or (= op LDX) (= op LDC)) (>= lop ST0) (< lop ADDS0))
+        (.set code (dec n) (insn op (bit-or M-PUSH (bit-shift-left (- lop ST0) 2)) b))
+
+        (and (pos? n) (>= op NEG) (<= op ABS) (= lop LDX))
+        (.set code (dec n) (insn op (bit-or la M-SRCX) b))
+
+        :else (.add code (insn op a b))))))
 
 (defn- konst! ^long [{:keys [^ArrayList consts overflow]} ^double v]
   (let [bits (Double/doubleToRawLongBits v)

@@ -1,4 +1,4 @@
-// compiler.cpp -- expression tree -> postfix bytecode (ISA v1, include/closyr_b200.h).
+// compiler.cpp -- expression tree -> postfix bytecode (ISA v1.1, include/closyr_b200.h).
 //
 // Lowering rules (frozen; the CPU oracle's tree walk applies the same per-node semantics):
 //   Plus/Times      left fold in argument order.  A leaf operand (x or a real literal) is
@@ -11,6 +11,7 @@
 //   Cot/Sec/Csc     TAN/COS/SIN followed by RECIP (Symja numericises them as reciprocals).
 //   Integer/Rational literals become doubles: correctly rounded integer, double(num)/double(den) (A8).
 //   No transcendental constant folding: the encoding must be bit-identical in every host language.
+//   Peephole (ISA v1.1): `ST0+k ; LDX|LDC` becomes the load with CL_M_PUSH, `LDX ; f` becomes f with CL_M_SRCX.
 #include "compiler.hpp"
 
 #include <cmath>
@@ -94,6 +95,18 @@ struct Emitter {
     void emit(int op, int a = 0, int b = 0)
     {
         if (p->code.size() + 8 > CLOSYR_MAX_CODE_WORDS) { overflow = true; return; }
+        if (!p->code.empty()) {                      // ISA v1.1 fusions (the code is straight-line)
+            const uint32_t last = p->code.back();
+            const int lop = (int)(last & 0xffu), la = (int)((last >> 8) & 0xffu);
+            if ((op == CL_LDX || op == CL_LDC) && lop >= CL_ST0 && lop < CL_ADDS0) {      // ST0+k ; LDX  ->  LDX push k
+                p->code.back() = CLOSYR_INSN(op, CL_M_PUSH | ((lop - CL_ST0) << 2), b);
+                return;
+            }
+            if (op >= CL_NEG && op <= CL_ABS && lop == CL_LDX) {                           // LDX ; f  ->  f(x)
+                p->code.back() = CLOSYR_INSN(op, la | CL_M_SRCX, b);
+                return;
+            }
+        }
         p->code.push_back(CLOSYR_INSN(op, a, b));
     }
     int konst(double v)

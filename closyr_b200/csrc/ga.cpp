@@ -74,7 +74,6 @@ NodeP g_plus(std::vector<NodeP> terms)
     if (s->kind != Kind::Plus) return s;
     struct Term { NodeP coef, body; };
     std::vector<Term> ts;
-    bool merged = false;
     for (auto &t : s->args) {
         Term cur;
         if (t->is_number()) { cur.coef = std::move(t); cur.body = nullptr; }
@@ -91,7 +90,7 @@ NodeP g_plus(std::vector<NodeP> terms)
             for (auto &o : ts)
                 if (o.body && same_expr(*o.body, *cur.body)) {
                     o.coef = num_add(*o.coef, *cur.coef);
-                    found = merged = true;
+                    found = true;
                     break;
                 }
         if (!found) ts.push_back(std::move(cur));
@@ -104,7 +103,6 @@ NodeP g_plus(std::vector<NodeP> terms)
         f.push_back(std::move(t.body));
         out.push_back(canon_times(std::move(f)));
     }
-    (void)merged;
     return canon_plus(std::move(out));
 }
 

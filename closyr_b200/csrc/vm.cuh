@@ -467,6 +467,10 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
         if (acc.re != acc.re) return acc;                   // Indeterminate absorbs every later instruction
+        if (op < CL_ST && (a & (CL_M_PUSH | CL_M_SRCX)) && op != CL_LDSPEC) {   // ISA v1.1 modifiers
+            if (a & CL_M_PUSH) slot[CL_M_PUSH_SLOT(a)] = acc;
+            if (a & CL_M_SRCX) acc = zv(x, 0.0);
+        }
         switch (op) {
         case CL_END: return acc;
         case CL_LDX: acc = zv(x, 0.0); break;
@@ -535,12 +539,22 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
 // ------------------------------------------------------------------------------------------------
 #define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
 
+// spill slots are addressed with a 32-bit shared-window address computed once per evaluation: through a generic
+// pointer the compiler rebuilds the window base (S2UR CgaCtaId, UMOV, UIADD3, ULEA) at every access
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 // All elementary-function instructions of the fast path, 4 points per call (the struct travels in registers):
 // four calls of the scalar routine per instruction, one copy of every routine in the kernel image.  Returns the values and the mask of points that need the complete algebra (see below).
 struct D4 { double v[4]; };
 struct R4 { D4 d; uint32_t ev; };
 
-__device__ __noinline__ R4 k1_unary(uint32_t op, D4 in, double c)
+__device__ __forceinline__ R4 k1_unary(uint32_t op, D4 in, double c)
 {
     R4 out;
     double a[4] = { in.v[0], in.v[1], in.v[2], in.v[3] };
@@ -577,18 +591,27 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
     uint32_t ev = 0;
     int pc = 0;
     uint32_t w = scode[0];
+    const uint32_t slot_base = (uint32_t)__cvta_generic_to_shared(sslot);
     CLOSYR_FORJ acc[j] = 0.0;
 #pragma unroll 1
     for (;;) {
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
         w = scode[++pc];                                     // prefetch (the buffer has one word of slack)
+        if (op < CL_ST && (a & (CL_M_PUSH | CL_M_SRCX)) && op != CL_LDSPEC) {
+            // ISA v1.1 modifiers of the leaf loads and the elementary functions: push acc, read x
+            if (a & CL_M_PUSH) {
+                const uint32_t sl = slot_base + CL_M_PUSH_SLOT(a) * (P * 32 * 8);
+                CLOSYR_FORJ sts_f64(sl + j * 256, acc[j]);
+            }
+            if (a & CL_M_SRCX) { CLOSYR_FORJ acc[j] = x[j]; }
+        }
         if (op >= CL_ST0) {
             // register-file-free slot forms: CL_ST0+a, CL_ADDS0+a, CL_MULS0+a with a in 0..3
-            double *sl = sslot + a * (P * 32);
-            if (op < CL_ADDS0) { CLOSYR_FORJ sl[j * 32] = acc[j]; }
-            else if (op < CL_MULS0) { CLOSYR_FORJ acc[j] = sl[j * 32] + acc[j]; }
-            else { CLOSYR_FORJ acc[j] = sl[j * 32] * acc[j]; }
+            const uint32_t sl = slot_base + a * (P * 32 * 8);
+            if (op < CL_ADDS0) { CLOSYR_FORJ sts_f64(sl + j * 256, acc[j]); }
+            else if (op < CL_MULS0) { CLOSYR_FORJ acc[j] = lds_f64(sl + j * 256) + acc[j]; }
+            else { CLOSYR_FORJ acc[j] = lds_f64(sl + j * 256) * acc[j]; }
             continue;
         }
         switch (op) {

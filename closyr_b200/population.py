@@ -115,8 +115,10 @@ OPNAMES = {
 }
 
 
-def disassemble(arrays, i):
-    """Human-readable listing of program i (used by tests and docs)."""
+def disassemble(arrays, i, expand=False):
+    """Human-readable listing of program i (used by tests and docs).  ISA v1.1 modifiers are shown as
+    `push k:` (slot[k] = acc first) and `f(x)` (the operand is x); expand=True lists the equivalent v1
+    instruction sequence instead (ST0+k ; LDX ; f)."""
     c0, c1 = int(arrays["code_off"][i]), int(arrays["code_off"][i + 1])
     k0 = int(arrays["const_off"][i])
     out = []
@@ -128,11 +130,25 @@ def disassemble(arrays, i):
             out.append("END")
             break
         if name in ("LDC", "ADDC", "MULC", "POWC", "LDZ"):
-            out.append("%s %r" % (name, float(arrays["consts"][k0 + b])))
+            text = "%s %r" % (name, float(arrays["consts"][k0 + b]))
         elif name == "POWI":
-            out.append("POWI %d" % (b - 65536 if b >= 32768 else b))
+            text = "POWI %d" % (b - 65536 if b >= 32768 else b)
         elif name in ("ST", "ADDS", "MULS", "POWS", "LDSPEC"):
-            out.append("%s %d" % (name, a))
+            text = "%s %d" % (name, a)
         else:
-            out.append(name)
+            text = name
+        modifiers = op in (1, 2) or 9 <= op <= 23
+        push = modifiers and (a & 2)
+        srcx = modifiers and 9 <= op <= 23 and (a & 1)
+        if expand:
+            if push:
+                out.append("ST%d" % ((a >> 2) & 3))
+            if srcx:
+                out.append("LDX")
+            out.append(text)
+        else:
+            if srcx:
+                head, _, rest = text.partition(" ")
+                text = head + "(x)" + ((" " + rest) if rest else "")
+            out.append(("push %d: " % ((a >> 2) & 3) if push else "") + text)
     return out

@@ -31,13 +31,23 @@ extern "C" {
 #define CLOSYR_DEFAULT_MAX_LEAFS 40
 
 /* ------------------------------------------------------------------------------------------------
- * Bytecode ISA v1 (frozen; DESIGN.md "Bytecode").  One instruction = one uint32:
- *     bits 0..7 opcode, bits 8..15 `a` (spill slot), bits 16..31 `b` (constant index or signed exponent).
+ * Bytecode ISA v1.1 (DESIGN.md "Bytecode").  One instruction = one uint32:
+ *     bits 0..7 opcode, bits 8..15 `a` (spill slot, or modifiers), bits 16..31 `b` (constant index or signed exponent).
  * The machine is a postfix evaluator whose top of stack is the accumulator `acc`; the rest of the
  * operand stack is addressed by STATIC slot numbers chosen by the compiler (the depth of a postfix
  * program is known at every instruction), so the kernel keeps slots 0..3 in registers.
  * Leaf operands (x, constants) are fused into the arithmetic instruction that consumes them.
+ *
+ * ISA v1.1 modifiers (a v1 program, all modifier bits 0, means what it meant).  The `a` field of the
+ * leaf loads CL_LDX / CL_LDC and of the elementary functions CL_NEG .. CL_ABS is a modifier byte:
+ *     CL_M_SRCX   elementary functions only: the operand is x, not acc         (was: LDX ; f)
+ *     CL_M_PUSH   before anything else, slot[(a >> 2) & 3] = acc               (was: ST0+k ; ...)
+ * so the very common  ST0 ; LDX ; SIN  is ONE instruction: SIN with a = CL_M_SRCX | CL_M_PUSH | 0 << 2.
+ * The compiler applies both fusions wherever they are possible; a third of all dispatches disappear.
  * ---------------------------------------------------------------------------------------------- */
+#define CL_M_SRCX 0x01
+#define CL_M_PUSH 0x02
+#define CL_M_PUSH_SLOT(a) (((a) >> 2) & 3)
 enum closyr_opcode {
     CL_END = 0,
     CL_LDX = 1,      /* acc = x                                                        */

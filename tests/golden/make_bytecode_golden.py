@@ -30,6 +30,7 @@ for text in corpus:
         "meta": "%08x" % int(a["meta"][0]),
         "aux": "%08x" % int(a["aux"][0]),
         "listing": cb.disassemble(a, 0),
+        "listing_v1": cb.disassemble(a, 0, expand=True),
     })
-json.dump({"isa": 1, "programs": out}, open(os.path.join(ROOT, "tests", "golden", "bytecode_golden.json"), "w"), indent=1)
+json.dump({"isa": "1.1", "programs": out}, open(os.path.join(ROOT, "tests", "golden", "bytecode_golden.json"), "w"), indent=1)
 print(len(out), "programs")

@@ -31,6 +31,8 @@ def test_bytecode_matches_golden_bit_for_bit():
         assert [struct.pack(">d", float(c)).hex() for c in a["consts"]] == g["consts"], g["text"]
         assert "%08x" % int(a["meta"][0]) == g["meta"] and "%08x" % int(a["aux"][0]) == g["aux"], g["text"]
         assert cb.to_fullform(g["text"]) == g["fullform"]
+        # the v1-equivalent instruction sequence (modifiers expanded) was frozen with ISA v1 and must not move
+        assert cb.disassemble(a, 0, expand=True) == g["listing_v1"], g["text"]
 
 
 def test_compiling_fullform_gives_the_same_program_as_the_printed_form():
@@ -69,8 +71,15 @@ def test_canonicalisation(text, fullform, leafs):
 
 def test_listing_of_the_mutation_test_expression():
     a = compile_one("-1+x+Cos(x)/Sqrt(x)-x*Sin(1/2-x)")
-    assert cb.disassemble(a, 0) == ["LDC -1.0", "ADDX", "ST0", "LDX", "COS", "ST1", "LDX", "RSQRT", "MULS1", "ADDS0", "ST0",
-                                    "LDC -1.0", "MULX", "ST1", "LDC -1.0", "MULX", "ADDC 0.5", "SIN", "MULS1", "ADDS0", "END"]
+    # the v1 instruction sequence the program stands for ...
+    assert cb.disassemble(a, 0, expand=True) == [
+        "LDC -1.0", "ADDX", "ST0", "LDX", "COS", "ST1", "LDX", "RSQRT", "MULS1", "ADDS0", "ST0",
+        "LDC -1.0", "MULX", "ST1", "LDC -1.0", "MULX", "ADDC 0.5", "SIN", "MULS1", "ADDS0", "END"]
+    # ... and the 14 instructions it is encoded in (ISA v1.1: stores fused into the next load, LDX into the function)
+    assert cb.disassemble(a, 0) == [
+        "LDC -1.0", "ADDX", "push 0: COS(x)", "push 1: RSQRT(x)", "MULS1", "ADDS0", "push 0: LDC -1.0", "MULX",
+        "push 1: LDC -1.0", "MULX", "ADDC 0.5", "SIN", "MULS1", "ADDS0", "END"]
+    assert [int(w) for w in a["code"][:4]] == [0x00000002, 0x00000005, 0x00000313, 0x0000070D]
     meta = int(a["meta"][0])
     assert meta & 0xFFFF == 22 and (meta >> 24) == 2 and ((meta >> 16) & 0xFF) == 0
 
