@@ -309,6 +309,17 @@ def main():
         "hbm_points_stream_GBps": (16.0 * n_points + h2d) / (dev_ms / args.steps * 1e-3) / 1e9,
     }
     try:
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command, per launch;
+        # only reported for the workload it was captured on
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        wl = tr["workload"]
+        if (wl["population"], wl["points"], wl["max_leafs"], wl["n_gpus"], wl["sharding"]) == (pop_n, n_points, max_leafs, world, args.shard):
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roof["algorithmic_bytes_per_launch"] = h2d + d2h + 16 * n_points
+    except Exception:
+        pass
+    try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roof["hbm_peak_GBps_measured"] = peaks.get("hbm_gbs")
     except Exception:
