@@ -339,3 +339,44 @@ def test_duplicates_score_bit_equal_at_baseline_size(ctx):
     order = ctx.rank(1000)
     assert (np.diff(s[order]) <= 0).all()
     assert s[order[0]] == s.max()
+
+
+# ------------------------------------------------------------------ the reference's own expression corpus
+def csv_style_points(n):
+    """SURVEY.md section 8d, second objective: piecewise data in the style of resources/csvs/test_inputs_*.csv
+    (a dozen hand-placed knots over a wide x range), linearly interpolated to n points."""
+    kx = np.array([0.0, 2.0, 5.0, 9.0, 14.0, 20.0, 27.0, 35.0, 44.0, 54.0])
+    ky = np.array([1.0, 1.5, 3.0, 0.0, -2.0, -12.0, -20.0, -24.0, -11.0, 4.0])
+    xs = np.linspace(kx[0], kx[-1], n)
+    return xs, np.interp(xs, kx, ky)
+
+
+def golden_corpus_population():
+    """SURVEY.md section 8d, second population source: the 96 golden results of ops_modify_test.clj:463-751 (plus the
+    strings of ops_test / ops_eval_test), their pairwise crossovers (modify.clj:142-196) and one more mutation of
+    each (initialize.clj:35-665) -- Symja-canonical shapes a real run produces."""
+    import json
+    import os
+    from closyr_b200 import ga as G
+    forms = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "symja_canonical_forms.json")))
+    base = [m["expr"] for m in forms["mutations"]] + [m["expr"] for m in forms["extra"]]
+    texts = [cb.to_fullform(t) for t in base]
+    n = len(base)
+    for k in range(400):
+        i, j = (7 * k + 3) % n, (13 * k + 5) % n
+        texts.append(G.crossover_expr(base[i], base[j], 60, seed=1000 + k))
+    for k in range(2 * n):
+        texts.append(G.mutate_expr(base[k % n], (5 * k + 1) % 96, seed=2000 + k))
+    return texts
+
+
+@pytest.mark.parametrize("points", ["synthetic", "csv-style"])
+def test_golden_corpus_with_crossovers_and_mutations(ctx, points):
+    xs, ys = synth_points(1024) if points == "synthetic" else csv_style_points(1024)
+    texts = golden_corpus_population()
+    assert len(texts) > 700
+    got, flags = gpu_scores(ctx, texts, xs, ys, 40)
+    want, ok = assert_population_scores_match(texts, xs, ys, 40, got, min_stable=0.4)
+    assert ((flags & L.R_TOO_BIG) != 0).tolist() == [O.leaf_count(t) > 40 for t in texts]
+    stable = np.nonzero(ok)[0]
+    assert int(stable[np.argmax(got[stable])]) == int(stable[np.argmax(want[stable])])     # same best expression
