@@ -78,7 +78,8 @@ struct DeviceState {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
-    DevBuf xs, ys, scores, rflags, partials, partials_all, flush, eval_xs, eval_f, eval_status, rank_a, rank_b;
+    DevBuf xs, ys, leaf_tab, scores, rflags, partials, partials_all, flush, eval_xs, eval_f, eval_status, rank_a, rank_b;
+    int64_t leaf_stride = 0;
     DevPop pop, eval_pop;
     int64_t chunk_lo = 0, chunk_hi = 0;   // point-sharded mode: this device's chunk range
 };
@@ -188,6 +189,8 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.pop = pv;
     sp.xs = (const double *)d.xs.p;
     sp.ys = (const double *)d.ys.p;
+    sp.leaf_tab = d.leaf_stride > 0 ? (const double *)d.leaf_tab.p : nullptr;
+    sp.leaf_stride = d.leaf_stride;
     sp.n = ctx->n_points;
     sp.chunk_begin = c_lo;
     sp.chunk_end = c_hi;
@@ -318,6 +321,14 @@ int closyr_set_points(closyr_ctx *ctx, const double *xs, const double *ys, int64
         if (n) {
             CU(ctx, cudaMemcpyAsync(d.xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
             CU(ctx, cudaMemcpyAsync(d.ys.p, ys, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+        }
+        // f(x_i) tables of the raw variable, shared by every expression of every generation scored on these points
+        d.leaf_stride = n_chunks_of(n) * CHUNK_POINTS;
+        if (d.leaf_stride > 0) {
+            CU(ctx, d.leaf_tab.reserve((size_t)d.leaf_stride * LEAF_TAB_ROWS * 8));
+            launch_leaf_table((const double *)d.xs.p, n, d.leaf_stride, (double *)d.leaf_tab.p, d.stream);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
         }
     }
     for (auto &d : ctx->devs) {

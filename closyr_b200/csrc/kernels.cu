@@ -52,6 +52,8 @@ struct Staged {
     const double *sconst;
     double *slvl;      // per-chunk sums of the tile (score_kernel) / scratch
     double *sslot;     // this lane's column of the warp's spill slots: [slot 0..3][point 0..3][lane]
+    const double *leaf_tab;    // f(x_i) tables of the resident points (ScoreParams), nullptr when xs are ad hoc
+    int64_t leaf_stride;
 };
 
 constexpr int SLOT_DOUBLES_PER_WARP = CLOSYR_REG_SLOTS * POINTS_PER_LANE * 32;
@@ -72,7 +74,7 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     for (uint32_t i = tid; i < nk; i += nthreads) sconst[i] = gk[i];
     for (uint32_t i = tid; i < ncode; i += nthreads) scode[i] = gc[i];
     if (tid == 0) scode[ncode] = 0;
-    Staged s = { scode, sconst, slvl, sslot };
+    Staged s = { scode, sconst, slvl, sslot, nullptr, 0 };
     return s;
 }
 
@@ -87,7 +89,7 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
 // wherever the fast path is valid, so the heuristic cannot change a score.
 // Must be called by every thread of the CTA (it contains __syncthreads).
 struct Round {
-    double *list;          // [warps * 128] reported x values, replaced in place by their results
+    double *list;          // [warps * 128] indices of the reported points, replaced in place by their results
     uint32_t *counts;      // [2][32] reported points per warp, double-buffered by round parity
 };
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
 #pragma unroll
             for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
         } else if (mode == 0 && !is_const) {
-            ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v) & valid;
+            ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v, st.leaf_tab ? st.leaf_tab + base : nullptr, st.leaf_stride) & valid;
             // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -149,10 +151,11 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
     uint32_t pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if ((ev >> j) & 1u) rd.list[pos++] = x[j];
+        if ((ev >> j) & 1u) rd.list[pos++] = __longlong_as_double(base + j);      // the point's index
     __syncthreads();
     for (uint32_t r = tid; r < total; r += blockDim.x) {
-        const Z z = run_full(st.scode, st.sconst, rd.list[r]);
+        const int64_t idx = __double_as_longlong(rd.list[r]);
+        const Z z = run_full(st.scode, st.sconst, xs[idx], st.leaf_tab ? st.leaf_tab + idx : nullptr, st.leaf_stride);
         const bool real = z.re == z.re && z.im == 0.0;
         rd.list[r] = real ? z.re : __longlong_as_double(0x7ff8000000000000ll);    // NaN marks "not a real number"
     }
@@ -220,7 +223,7 @@ __device__ __forceinline__ Staged stage_program_tma(const DevPopulation &pop, in
     }
     __syncthreads();                 // the initialised barrier is visible to every waiter
     mbar_wait(bar, 0);
-    Staged s = { scode, sconst, slvl, sslot };
+    Staged s = { scode, sconst, slvl, sslot, nullptr, 0 };
     return s;
 }
 
@@ -253,7 +256,9 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     }
 
     __shared__ __align__(8) unsigned long long s_bar;
-    const Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS, &s_bar);
+    Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS, &s_bar);
+    st.leaf_tab = p.leaf_tab;
+    st.leaf_stride = p.leaf_stride;
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -481,9 +486,37 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters)
     out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// f(x_i) for the parameter-free elementary functions of the raw variable, through the very routine the
+// interpreter's fast path calls (k1_unary), so a table entry is bit-identical to computing it in score_kernel.
+// Entries past n (the table is padded to whole chunks) take x = 1.0, as the kernel does for absent points.
+__global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restrict__ xs, int64_t n, int64_t stride,
+                                                           double *__restrict__ tab)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = q * 4;
+    if (i0 >= stride) return;
+    D4 in;
+#pragma unroll
+    for (int j = 0; j < 4; j++) in.v[j] = (i0 + j < n) ? xs[i0 + j] : 1.0;
+    for (uint32_t op = CL_RECIP; op <= CL_ACOS; op++) {
+        if (!((LEAF_TAB_MASK >> (op - CL_RECIP)) & 1u)) continue;
+        const R4 r = k1_unary(op, in, 0.0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) tab[(int64_t)(op - CL_RECIP) * stride + i0 + j] = r.d.v[j];
+    }
+}
+
 }  // namespace
 
 int score_warps(int32_t chunks_per_tile);
+
+void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab, void *stream)
+{
+    if (stride <= 0) return;
+    const int threads = 128;
+    const int64_t quads = stride / 4;
+    leaf_table_kernel<<<(unsigned)((quads + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(xs, n, stride, tab);
+}
 
 void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
 {

@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include "../../include/closyr_b200.h"
+
 namespace closyr {
 
 constexpr int CHUNK_POINTS = 128;     // 32 lanes x 4 consecutive points: the leaf of the fixed reduction tree
@@ -33,7 +35,17 @@ struct ScoreParams {
     uint8_t *rflags;                  // [n_expr]
     double *partials;                 // [n_tiles][n_expr][3] = sum, max, non-real count
     int64_t partial_tile_offset;      // index of this launch's first tile inside `partials`
+    // f(x_i) of the raw variable for the parameter-free elementary functions, tabulated once per closyr_set_points
+    // (every expression of every generation shares the points): row (op - CL_RECIP) of LEAF_TAB_ROWS rows of
+    // `leaf_stride` doubles; nullptr = compute in the kernel
+    const double *leaf_tab;
+    int64_t leaf_stride;
 };
+
+constexpr int LEAF_TAB_ROWS = CL_ACOS - CL_RECIP + 1;
+// RECIP SQRT RSQRT EXP LOG SIN COS TAN ASIN ACOS (bit = op - CL_RECIP); SQR, POWI and POWC are not tabulated
+constexpr uint32_t LEAF_TAB_MASK = 0x1FCDu;
+void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab, void *stream);
 
 struct FinalizeParams {
     const uint32_t *meta;

@@ -457,7 +457,10 @@ __device__ __noinline__ Z u_full(uint32_t op, Z a, double c)
         if (acc.im == 0.0 && (cond)) { acc.re = (fast); break; } \
         CLOSYR_ZSET(zf(acc))                                \
     }
-__device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x)
+// `tab` (or nullptr) points at this point's column of the f(x_i) tables (kernels.cuh): an elementary function of
+// the raw variable takes its value from there whenever it would have called the real routine.
+__device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x,
+                                   const double *__restrict__ tab, int64_t tab_stride)
 {
     Z slot[CLOSYR_MAX_SLOTS];
     Z acc = zv(0.0, 0.0);
@@ -471,6 +474,9 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
             if (a & CL_M_PUSH) slot[CL_M_PUSH_SLOT(a)] = acc;
             if (a & CL_M_SRCX) acc = zv(x, 0.0);
         }
+        const double *t = nullptr;
+        if ((a & CL_M_SRCX) && tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u))
+            t = tab + (op - CL_RECIP) * tab_stride;
         // the frequent instructions first (slot forms 35 %, Sin/Cos 30 % of all dispatches): the switch below
         // compiles to a compare tree
         if (op >= CL_ST0) {
@@ -481,7 +487,7 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
             continue;
         }
         if (op == CL_SIN || op == CL_COS) {
-            if (acc.im == 0.0) acc.re = m_sincos(acc.re, (int)(op - CL_SIN));
+            if (acc.im == 0.0) acc.re = t ? *t : m_sincos(acc.re, (int)(op - CL_SIN));
             else acc = op == CL_SIN ? zsin(acc) : zcos(acc);
             continue;
         }
@@ -497,9 +503,9 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         case CL_MULC: if (acc.im == 0.0) { acc.re *= sconst[b]; break; } CLOSYR_ZSET(lean_mul(acc, zv(sconst[b], 0.0)))
         case CL_NEG: CLOSYR_REAL1(true, -x_, zneg)
         case CL_SQR: if (acc.im == 0.0) { acc.re = acc.re * acc.re; break; } CLOSYR_ZSET(lean_mul(acc, acc))
-        case CL_RECIP: CLOSYR_REAL1(x_ != 0.0, m_recip(x_), zrecip)
-        case CL_SQRT: CLOSYR_REAL1(x_ >= 0.0, m_sqrt(x_), zsqrt)
-        case CL_RSQRT: if (acc.im == 0.0 && acc.re > 0.0) { acc.re = m_recip(m_sqrt(acc.re)); break; } CLOSYR_ZSET(zrecip(zsqrt(acc)))
+        case CL_RECIP: CLOSYR_REAL1(x_ != 0.0, t ? *t : m_recip(x_), zrecip)
+        case CL_SQRT: CLOSYR_REAL1(x_ >= 0.0, t ? *t : m_sqrt(x_), zsqrt)
+        case CL_RSQRT: if (acc.im == 0.0 && acc.re > 0.0) { acc.re = t ? *t : m_recip(m_sqrt(acc.re)); break; } CLOSYR_ZSET(zrecip(zsqrt(acc)))
         case CL_POWI: {
             const int n = (int)(short)b;
             if (acc.im == 0.0) {
@@ -516,11 +522,11 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
             if (acc.im == 0.0 && acc.re > 0.0 && !is_inf(acc.re) && !nonfinite(c) && c != 0.0) { acc.re = u_real(CL_POWC, acc.re, c); break; }
             CLOSYR_ZSET(zpow(acc, zmk(c, 0.0)))
         }
-        case CL_EXP: CLOSYR_REAL1(true, m_exp(x_), zexp)
-        case CL_LOG: CLOSYR_REAL1(x_ > 0.0, m_log(x_), zlog)
-        case CL_TAN: CLOSYR_REAL1(true, u_real(CL_TAN, x_, 0.0), ztan)
-        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, u_real(CL_ASIN, x_, 0.0), zasin)
-        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, u_real(CL_ACOS, x_, 0.0), zacos)
+        case CL_EXP: CLOSYR_REAL1(true, t ? *t : m_exp(x_), zexp)
+        case CL_LOG: CLOSYR_REAL1(x_ > 0.0, t ? *t : m_log(x_), zlog)
+        case CL_TAN: CLOSYR_REAL1(true, t ? *t : u_real(CL_TAN, x_, 0.0), ztan)
+        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : u_real(CL_ASIN, x_, 0.0), zasin)
+        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : u_real(CL_ACOS, x_, 0.0), zacos)
         case CL_ABS: CLOSYR_REAL1(true, fabs(x_), zabs)
         default: {
             // slot instructions: `a` is the slot for both the generic and the register forms
@@ -597,7 +603,8 @@ __device__ __forceinline__ R4 k1_unary(uint32_t op, D4 in, double c)
 // 40-register state at every dispatch (36 % of all issued instructions were IMAD.MOV, ncu profile r01_c).
 template <int P>
 __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
-                                             double *__restrict__ sslot, const double (&x)[P], double (&acc)[P])
+                                             double *__restrict__ sslot, const double (&x)[P], double (&acc)[P],
+                                             const double *__restrict__ tab, int64_t tab_stride)
 {
     double ls[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];    // deep spill slots: local memory, rarely touched
     uint32_t ev = 0;
@@ -659,11 +666,22 @@ __device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode,
                 if (nonfinite(c) || c == 0.0) { ev = (1u << P) - 1u; break; }
             }
             static_assert(P == 4, "k1_unary is written for 4 points per lane");
-            D4 in;
-            CLOSYR_FORJ in.v[j] = acc[j];
-            const R4 r = k1_unary(op, in, c);
-            CLOSYR_FORJ acc[j] = r.d.v[j];
-            ev |= r.ev;
+            if ((a & CL_M_SRCX) && tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u)) {
+                // f(x) of the raw variable: tabulated per point by leaf_table_kernel with the same routines
+                // (`tab` points at this lane's first point); the report rule is k1_unary's
+                const double2 t0 = *reinterpret_cast<const double2 *>(tab + (op - CL_RECIP) * tab_stride);
+                const double2 t1 = *reinterpret_cast<const double2 *>(tab + (op - CL_RECIP) * tab_stride + 2);
+                acc[0] = t0.x; acc[1] = t0.y; acc[2] = t1.x; acc[3] = t1.y;
+                uint32_t e4 = 0;
+                CLOSYR_FORJ if (is_inf(x[j]) || (acc[j] != acc[j] && x[j] == x[j])) e4 |= 1u << j;
+                ev |= e4;
+            } else {
+                D4 in;
+                CLOSYR_FORJ in.v[j] = acc[j];
+                const R4 r = k1_unary(op, in, c);
+                CLOSYR_FORJ acc[j] = r.d.v[j];
+                ev |= r.ev;
+            }
             // points are sorted by x, so a domain exit usually takes whole chunks: once every point of the warp is
             // reported the rest of the fast pass is wasted work (the complete algebra starts over anyway)
             if (__all_sync(0xffffffffu, ev == (1u << P) - 1u)) return ev;
