@@ -470,21 +470,22 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
         const int b = (int)(w >> 16);
         if (acc.re != acc.re) return acc;                   // Indeterminate absorbs every later instruction
-        if (op < CL_ST && (a & (CL_M_PUSH | CL_M_SRCX)) && op != CL_LDSPEC) {   // ISA v1.1 modifiers
-            if (a & CL_M_PUSH) slot[CL_M_PUSH_SLOT(a)] = acc;
-            if (a & CL_M_SRCX) acc = zv(x, 0.0);
-        }
-        const double *t = nullptr;
-        if ((a & CL_M_SRCX) && tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u))
-            t = tab + (op - CL_RECIP) * tab_stride;
-        // the frequent instructions first (slot forms 35 %, Sin/Cos 30 % of all dispatches): the switch below
-        // compiles to a compare tree
+        // the frequent instructions first (slot forms, then Sin/Cos): the switch below compiles to a compare tree
         if (op >= CL_ST0) {
             if (op < CL_ADDS0) { slot[a] = acc; continue; }
             const Z sl = slot[a];
             if (sl.im == 0.0 && acc.im == 0.0) acc.re = op < CL_MULS0 ? sl.re + acc.re : sl.re * acc.re;
             else acc = op < CL_MULS0 ? lean_add(sl, acc) : lean_mul(sl, acc);
             continue;
+        }
+        const double *t = nullptr;
+        if ((a & (CL_M_PUSH | CL_M_SRCX)) && op < CL_ST && op != CL_LDSPEC) {   // ISA v1.1 modifiers
+            if (a & CL_M_PUSH) slot[CL_M_PUSH_SLOT(a)] = acc;
+            if (a & CL_M_SRCX) {
+                acc = zv(x, 0.0);
+                if (tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u))
+                    t = tab + (op - CL_RECIP) * tab_stride;
+            }
         }
         if (op == CL_SIN || op == CL_COS) {
             if (acc.im == 0.0) acc.re = t ? *t : m_sincos(acc.re, (int)(op - CL_SIN));
