@@ -6,7 +6,7 @@
    the same constant pool (first-use order, de-duplicated by bit pattern) and the same meta/aux words for
    the same tree; tests/golden/bytecode_golden.json holds the expected encoding for 126 expressions
    (the 96 mutation outputs of test/closyr/ops_modify_test.clj among them).  It cannot be executed in the
-   build environment of this repository (no JVM); `closyr.gpu.compile-test` replays the golden file."
+   build environment of this repository (no JVM); `closyr.gpu.compile-test` (clj/test/closyr/gpu/compile_test.clj) replays the golden file."
   (:import
     (org.matheclipse.core.interfaces IAST IExpr IFraction IInteger INum ISymbol IComplex)
     (org.matheclipse.core.expression F S)
