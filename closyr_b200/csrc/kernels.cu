@@ -316,15 +316,12 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         for (int i = lane * 2 * stride; i + stride < cnt; i += 64 * stride) st.slvl[i] = st.slvl[i] + st.slvl[i + stride];
         __syncwarp();
     }
+    // max, counts and flags of the warps: one lane per warp, then shuffles (all three are order-independent)
+    double tile_max = warp_max(lane < nwarps ? s_max[lane] : 0.0);
+    const uint32_t tile_nonreal = __reduce_add_sync(FULL, lane < nwarps ? s_nonreal[lane] : 0u);
+    const uint32_t tile_full = __reduce_or_sync(FULL, lane < nwarps ? s_full[lane] : 0u);
     if (lane != 0) return;
     const double tile_sum = cnt > 0 ? st.slvl[0] : 0.0;
-    double tile_max = 0.0;
-    uint32_t tile_nonreal = 0, tile_full = 0;
-    for (int w = 0; w < nwarps; w++) {
-        tile_max = fmax(tile_max, s_max[w]);
-        tile_nonreal += s_nonreal[w];
-        tile_full |= s_full[w];
-    }
     if (p.final_scores) {
         uint8_t rf = tile_full ? CL_R_FULL_SEMANTICS : 0;
         double score;
