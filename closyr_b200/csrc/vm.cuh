@@ -397,58 +397,10 @@ __device__ __noinline__ Z zpow(Z z, Z w)
     return zexp(zmul(w, zlog(z)));
 }
 
-// ------------------------------------------------------------------------------------------------
-// complete value algebra, one instruction applied to one value.  On the real line (im == 0: finite reals,
-// directed infinities, and Indeterminate as re = NaN) an instruction takes the same IEEE sequence as the fast
-// path whenever that is the algebra's answer; poles, domain exits and genuinely complex operands go to z*.
-// ------------------------------------------------------------------------------------------------
-__device__ __noinline__ Z u_full(uint32_t op, Z a, double c)
-{
-    if (a.im == 0.0) {
-        const double x = a.re;
-        switch (op) {
-        case CL_NEG: return zv(-x, 0.0);
-        case CL_SQR: return zv(x * x, 0.0);
-        case CL_RECIP: if (x != 0.0) return zv(k_recip(x), 0.0); break;
-        case CL_SQRT: if (x >= 0.0) return zv(k_sqrt(x), 0.0); break;
-        case CL_RSQRT: if (x > 0.0) return zv(u_real(CL_RSQRT, x, 0.0), 0.0); break;
-        case CL_POWI: {
-            const int n = (int)c;
-            const double r = u_real(CL_POWI, x, n < 0 ? -c : c);
-            if (n > 0) return zv(r, 0.0);
-            if (r != 0.0) return zv(k_recip(r), 0.0);
-            return zcinf();
-        }
-        case CL_POWC: if (x > 0.0 && !is_inf(x) && !nonfinite(c) && c != 0.0) return zv(k_pow(x, c), 0.0); break;
-        case CL_LOG: if (x > 0.0) return zv(k_log(x), 0.0); break;
-        case CL_ASIN:
-        case CL_ACOS: if (fabs(x) <= 1.0) return zv(u_real(op, x, 0.0), 0.0); break;
-        default: return zv(u_real(op, x, 0.0), 0.0);      // EXP SIN COS TAN ABS: total on the real line
-        }
-    }
-    switch (op) {
-    case CL_NEG: return zneg(a);
-    case CL_SQR: return zmul(a, a);
-    case CL_RECIP: return zrecip(a);
-    case CL_SQRT: return zsqrt(a);
-    case CL_RSQRT: return zrecip(zsqrt(a));
-    case CL_POWI: return zpowi(a, (int)c);
-    case CL_POWC: return zpow(a, zmk(c, 0.0));
-    case CL_EXP: return zexp(a);
-    case CL_LOG: return zlog(a);
-    case CL_SIN: return zsin(a);
-    case CL_COS: return zcos(a);
-    case CL_TAN: return ztan(a);
-    case CL_ASIN: return zasin(a);
-    case CL_ACOS: return zacos(a);
-    default: return zabs(a);
-    }
-}
-
 // One point through the program with the complete algebra: only the points the fast path reported come
 // here.  Flat on purpose -- one switch, the real-line case of every instruction inline (the same IEEE sequence
 // as the fast path, through the same m_* routines), one call into z* only when a value is off the real line.
-// A first version went run_full -> u_full -> u_real -> m_*: 125 instructions per point-instruction and an
+// A first version went through one generic per-value routine and then u_real -> m_*: 125 instructions per point-instruction and an
 // instruction-fetch stall at almost every step (ncu profile r01_f).
 #define CLOSYR_ZSET(expr) { acc = (expr); break; }
 #define CLOSYR_REAL1(cond, fast, zf)                        \
