@@ -58,6 +58,8 @@ enum { U_SINH = 100, U_COSH = 101 };
 __device__ __noinline__ double m_exp(double x) { double t[1] = { x }; v_exp<1>(t); return t[0]; }
 __device__ __noinline__ double m_log(double x) { double t[1] = { x }; v_log<1>(t); return t[0]; }
 __device__ __noinline__ double m_sincos(double x, int shift) { double t[1] = { x }; v_sincos<1>(t, shift); return t[0]; }
+struct SC { double s, c; };
+__device__ __noinline__ SC m_sincos_both(double x) { SC r; v_sincos_both(x, r.s, r.c); return r; }
 __device__ __noinline__ double m_recip(double x) { return 1.0 / x; }
 __device__ __noinline__ double m_sqrt(double x) { return sqrt(x); }
 
@@ -233,7 +235,8 @@ __device__ __noinline__ Z zexp(Z a)
     if (t == T_INDET || t == T_CINF) return zindet();
     if (t == T_REAL) return zmk(k_exp(a.re), 0.0);
     double e = k_exp(a.re);
-    return zmk(e * k_cos(a.im), e * k_sin(a.im));
+    const SC sc = m_sincos_both(a.im);
+    return zmk(e * sc.c, e * sc.s);
 }
 
 __device__ __noinline__ Z zlog(Z a)
@@ -255,7 +258,8 @@ __device__ __noinline__ Z zsin(Z a)
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
     if (t == T_REAL) return zmk(k_sin(a.re), 0.0);
-    return zmk(k_sin(a.re) * k_cosh(a.im), k_cos(a.re) * k_sinh(a.im));
+    const SC sc = m_sincos_both(a.re);
+    return zmk(sc.s * k_cosh(a.im), sc.c * k_sinh(a.im));
 }
 
 __device__ __noinline__ Z zcos(Z a)
@@ -263,7 +267,8 @@ __device__ __noinline__ Z zcos(Z a)
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
     if (t == T_REAL) return zmk(k_cos(a.re), 0.0);
-    return zmk(k_cos(a.re) * k_cosh(a.im), -(k_sin(a.re) * k_sinh(a.im)));
+    const SC sc = m_sincos_both(a.re);
+    return zmk(sc.c * k_cosh(a.im), -(sc.s * k_sinh(a.im)));
 }
 
 __device__ __noinline__ Z ztan(Z a)
@@ -274,8 +279,9 @@ __device__ __noinline__ Z ztan(Z a)
     if (a.im > 20.0) return zv(0.0, 1.0);
     if (a.im < -20.0) return zv(0.0, -1.0);
     double a2 = 2.0 * a.re, b2 = 2.0 * a.im;
-    double d = k_cos(a2) + k_cosh(b2);
-    return zmk(k_sin(a2) / d, k_sinh(b2) / d);
+    const SC sc = m_sincos_both(a2);
+    double d = sc.c + k_cosh(b2);
+    return zmk(sc.s / d, k_sinh(b2) / d);
 }
 
 __device__ __forceinline__ Z zmul_i(Z a) { return zmk(-a.im, a.re); }
