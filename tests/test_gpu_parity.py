@@ -380,3 +380,18 @@ def test_golden_corpus_with_crossovers_and_mutations(ctx, points):
     assert ((flags & L.R_TOO_BIG) != 0).tolist() == [O.leaf_count(t) > 40 for t in texts]
     stable = np.nonzero(ok)[0]
     assert int(stable[np.argmax(got[stable])]) == int(stable[np.argmax(want[stable])])     # same best expression
+
+
+@pytest.mark.parametrize("seed,mix", [(31, 0), (32, 1), (33, 0)])
+def test_generated_expressions_on_extreme_points(ctx, seed, mix):
+    """Random expressions on the points where IEEE arithmetic and the value algebra part ways: signed zeros,
+    denormals, huge magnitudes and both infinities (ops_eval_test.clj:161-173 pins x = +Inf and x - Infinity)."""
+    xs = np.array([-np.inf, -1e308, -1e154, -1e6, -3.0, -1.0, -0.5, -1e-300, -5e-324, -0.0, 0.0, 5e-324, 1e-300,
+                   0.5, 1.0, 2.0, 710.0, 1e6, 1e154, 1e308, np.inf])
+    b = cb.PopulationBuilder()
+    texts = b.generate(seed, 300, 30, mix, want_texts=True)
+    f, status = ctx.eval_batch(b.view(), xs)
+    check_eval_against_oracle(texts, xs, f, status)
+    ys = np.linspace(-2.0, 2.0, len(xs))
+    got, _ = gpu_scores(ctx, texts, xs, ys, 40)
+    assert_population_scores_match(texts, xs, ys, 40, got, min_stable=0.3)
