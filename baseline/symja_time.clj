@@ -32,10 +32,14 @@
                       (mapv (fn [line]
                               ;; the file holds the variable as `x`; closyr's own symbol is (F/Dummy "x")
                               (ops-common/->phenotype x (.subs (.parse parser line) x-text x) nil))))
-      run-args   (#'sr/->run-args {:input-xs-exprs (ops-common/doubles->exprs xs)
-                                   :input-xs-vec   xs
-                                   :input-ys-exprs (ops-common/doubles->exprs ys)
-                                   :input-ys-vec   ys})
+      ;; ->run-args insists on :iters and a population count/phenos (symbolic_regression.clj:355-383); note that the
+      ;; reference's schema caps points at 10000 and the population at 100000 (spec.clj:140-145, row N3)
+      run-args   (sr/->run-args {:input-xs-exprs     (ops-common/doubles->exprs xs)
+                                 :input-xs-vec       xs
+                                 :input-ys-vec       ys
+                                 :iters              1
+                                 :input-phenos-count (count phenos)
+                                 :max-leafs          max-leafs})
       run-config {:max-leafs max-leafs}
       score      (partial ops/score-fn run-args run-config)
       cores      (.availableProcessors (Runtime/getRuntime))]
