@@ -52,7 +52,6 @@ __device__ __forceinline__ double powi_real(double a, int n)
     return n < 0 ? 1.0 / r : r;
 }
 
-enum { U_SINH = 100, U_COSH = 101 };
 
 // scalar entry points of the lean routines (vmath.cuh): a few hundred bytes each, shared by both evaluators
 __device__ __noinline__ double m_exp(double x) { double t[1] = { x }; v_exp<1>(t); return t[0]; }
@@ -79,10 +78,24 @@ __device__ __noinline__ double u_real(uint32_t op, double a, double c)
     case CL_TAN: return tan(a);
     case CL_ASIN: return asin(a);
     case CL_ACOS: return acos(a);
-    case U_SINH: return sinh(a);
-    case U_COSH: return cosh(a);
     default: return fabs(a);            // CL_ABS
     }
+}
+// sinh and cosh of the same argument (the complex sin / cos / tan need both): one exponential where that is
+// accurate (0.5 <= |y| < 700: e - 1/e cancels at most one bit there), the library routines elsewhere
+__device__ __noinline__ SC m_sinhcosh(double y)
+{
+    SC r;
+    const double ay = fabs(y);
+    if (ay >= 0.5 && ay < 700.0) {
+        const double e = m_exp(ay), ei = m_recip(e);
+        r.c = 0.5 * e + 0.5 * ei;
+        r.s = copysign(0.5 * e - 0.5 * ei, y);
+    } else {
+        r.s = sinh(y);
+        r.c = cosh(y);
+    }
+    return r;
 }
 #define k_sin(x) u_real(CL_SIN, (x), 0.0)
 #define k_cos(x) u_real(CL_COS, (x), 0.0)
@@ -92,8 +105,6 @@ __device__ __noinline__ double u_real(uint32_t op, double a, double c)
 #define k_asin(x) u_real(CL_ASIN, (x), 0.0)
 #define k_acos(x) u_real(CL_ACOS, (x), 0.0)
 #define k_pow(x, y) u_real(CL_POWC, (x), (y))
-#define k_sinh(x) u_real(U_SINH, (x), 0.0)
-#define k_cosh(x) u_real(U_COSH, (x), 0.0)
 #define k_recip(x) u_real(CL_RECIP, (x), 0.0)
 #define k_sqrt(x) u_real(CL_SQRT, (x), 0.0)
 __device__ __noinline__ double k_hypot(double x, double y) { return hypot(x, y); }
@@ -258,8 +269,8 @@ __device__ __noinline__ Z zsin(Z a)
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
     if (t == T_REAL) return zmk(k_sin(a.re), 0.0);
-    const SC sc = m_sincos_both(a.re);
-    return zmk(sc.s * k_cosh(a.im), sc.c * k_sinh(a.im));
+    const SC sc = m_sincos_both(a.re), h = m_sinhcosh(a.im);
+    return zmk(sc.s * h.c, sc.c * h.s);
 }
 
 __device__ __noinline__ Z zcos(Z a)
@@ -267,8 +278,8 @@ __device__ __noinline__ Z zcos(Z a)
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
     if (t == T_REAL) return zmk(k_cos(a.re), 0.0);
-    const SC sc = m_sincos_both(a.re);
-    return zmk(sc.c * k_cosh(a.im), -(sc.s * k_sinh(a.im)));
+    const SC sc = m_sincos_both(a.re), h = m_sinhcosh(a.im);
+    return zmk(sc.c * h.c, -(sc.s * h.s));
 }
 
 __device__ __noinline__ Z ztan(Z a)
@@ -279,9 +290,9 @@ __device__ __noinline__ Z ztan(Z a)
     if (a.im > 20.0) return zv(0.0, 1.0);
     if (a.im < -20.0) return zv(0.0, -1.0);
     double a2 = 2.0 * a.re, b2 = 2.0 * a.im;
-    const SC sc = m_sincos_both(a2);
-    double d = sc.c + k_cosh(b2);
-    return zmk(sc.s / d, k_sinh(b2) / d);
+    const SC sc = m_sincos_both(a2), h = m_sinhcosh(b2);
+    double d = sc.c + h.c;
+    return zmk(sc.s / d, h.s / d);
 }
 
 __device__ __forceinline__ Z zmul_i(Z a) { return zmk(-a.im, a.re); }
