@@ -256,3 +256,34 @@ def test_evolve_requires_scores_and_commit_requires_pending():
         L.check(L.lib().closyr_ga_evolve(ga._h, None))
     with pytest.raises(L.ClosyrError):
         L.check(L.lib().closyr_ga_commit_scores(ga._h, None, 3))
+
+
+# ------------------------------------------------------------------------------------ F/D restated
+def test_derivative_operator_agrees_with_finite_differences():
+    """The "Derivative" operator (initialize.clj:39-42, F/D) on generated expressions: the oracle's value of the
+    derived expression must match a central finite difference of the oracle's value of the original, wherever both
+    are smooth real functions around the point."""
+    import closyr_b200 as cb
+    idx = {label: i for i, (_, label) in enumerate(G.mutations())}["Derivative"]
+    b = cb.PopulationBuilder()
+    texts = b.generate(77, 300, 14, 0, want_texts=True)
+    xs = np.array([0.37, 0.81, 1.23, 1.9, 2.6])
+    h = 1e-6
+    checked = 0
+    for t in texts:
+        d = G.mutate_expr(t, idx)
+        f0, fm, fp = (O.eval_vec_pheno(t, xs + k) for k in (0.0, -h, h))
+        fd = O.eval_vec_pheno(d, xs)
+        if f0 is None or fm is None or fp is None or fd is None:
+            continue
+        for k in range(len(xs)):
+            vals = (f0[k], fm[k], fp[k], fd[k])
+            if not all(np.isfinite(v) for v in vals) or max(abs(v) for v in vals) > 1e6:
+                continue
+            num = (fp[k] - fm[k]) / (2 * h)
+            curv = abs(fp[k] - 2 * f0[k] + fm[k]) / (h * h)          # skip points next to a pole or a kink
+            if curv > 1e4:
+                continue
+            assert abs(num - fd[k]) <= 1e-4 * max(1.0, abs(fd[k])), (t, d, xs[k], num, fd[k])
+            checked += 1
+    assert checked > 500
