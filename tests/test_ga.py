@@ -287,3 +287,27 @@ def test_derivative_operator_agrees_with_finite_differences():
             assert abs(num - fd[k]) <= 1e-4 * max(1.0, abs(fd[k])), (t, d, xs[k], num, fd[k])
             checked += 1
     assert checked > 500
+
+
+def test_every_operator_yields_a_valid_phenotype_for_many_seeds():
+    """Property: whatever an operator returns parses again, has the leafCount the oracle's own reader computes
+    (two implementations of Symja's leafCount), is already in evaluated form (re-applying the canonicaliser is the
+    identity on its text) and compiles to a scorable program (no `unsupported` flag)."""
+    import closyr_b200 as cb
+    bases = [TEST_EXPR, "x", "1/2", "Sin(x)^2+Cos(x)^2", "E^(x*Log(x))-1/(x-2)", GOLDEN[85]["expr"], GOLDEN[64]["expr"]]
+    texts = []
+    for base in bases:
+        for index in range(96):
+            for seed in (1, 2, 3, 888):
+                texts.append(G.mutate_expr(base, index, seed=seed))
+    uniq = sorted(set(texts))
+    assert len(uniq) > 300
+    b = cb.PopulationBuilder()
+    b.add_many(uniq)
+    a = b.arrays()
+    for i, t in enumerate(uniq):
+        assert cb.leaf_count(t) == O.leaf_count(t), t
+        assert cb.to_fullform(t) == t, t
+        meta = int(a["meta"][i])
+        assert meta & 0xFFFF == min(cb.leaf_count(t), 65535)
+        assert not ((meta >> 16) & 0x02), t                      # CL_F_UNSUPPORTED
