@@ -97,16 +97,16 @@ __device__ __noinline__ SC m_sinhcosh(double y)
     }
     return r;
 }
-#define k_sin(x) u_real(CL_SIN, (x), 0.0)
-#define k_cos(x) u_real(CL_COS, (x), 0.0)
+#define k_sin(x) m_sincos((x), 0)
+#define k_cos(x) m_sincos((x), 1)
 #define k_tan(x) u_real(CL_TAN, (x), 0.0)
-#define k_exp(x) u_real(CL_EXP, (x), 0.0)
-#define k_log(x) u_real(CL_LOG, (x), 0.0)
+#define k_exp(x) m_exp(x)
+#define k_log(x) m_log(x)
 #define k_asin(x) u_real(CL_ASIN, (x), 0.0)
 #define k_acos(x) u_real(CL_ACOS, (x), 0.0)
 #define k_pow(x, y) u_real(CL_POWC, (x), (y))
-#define k_recip(x) u_real(CL_RECIP, (x), 0.0)
-#define k_sqrt(x) u_real(CL_SQRT, (x), 0.0)
+#define k_recip(x) m_recip(x)
+#define k_sqrt(x) m_sqrt(x)
 __device__ __noinline__ double k_hypot(double x, double y) { return hypot(x, y); }
 __device__ __noinline__ double k_atan2(double y, double x) { return atan2(y, x); }
 
