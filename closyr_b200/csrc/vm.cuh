@@ -62,7 +62,14 @@ __device__ __noinline__ SC m_sincos_both(double x) { SC r; v_sincos_both(x, r.s,
 __device__ __noinline__ double m_recip(double x) { return 1.0 / x; }
 __device__ __noinline__ double m_sqrt(double x) { return sqrt(x); }
 
-// real elementary function `op` of a (c = the literal operand of POWI / POWC)
+// the library routines that have no lean version: one copy each, called directly by both evaluators
+__device__ __noinline__ double m_tan(double x) { return tan(x); }
+__device__ __noinline__ double m_asin(double x) { return asin(x); }
+__device__ __noinline__ double m_acos(double x) { return acos(x); }
+__device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
+
+// real elementary function `op` of a (c = the literal operand of POWI / POWC): the generic entry, used where the
+// operation is not known at compile time
 __device__ __noinline__ double u_real(uint32_t op, double a, double c)
 {
     switch (op) {
@@ -70,14 +77,14 @@ __device__ __noinline__ double u_real(uint32_t op, double a, double c)
     case CL_SQRT: return m_sqrt(a);
     case CL_RSQRT: return m_recip(m_sqrt(a));
     case CL_POWI: return powi_real(a, (int)c);
-    case CL_POWC: return pow(a, c);
+    case CL_POWC: return m_pow(a, c);
     case CL_EXP: return m_exp(a);
     case CL_LOG: return m_log(a);
     case CL_SIN: return m_sincos(a, 0);
     case CL_COS: return m_sincos(a, 1);
-    case CL_TAN: return tan(a);
-    case CL_ASIN: return asin(a);
-    case CL_ACOS: return acos(a);
+    case CL_TAN: return m_tan(a);
+    case CL_ASIN: return m_asin(a);
+    case CL_ACOS: return m_acos(a);
     default: return fabs(a);            // CL_ABS
     }
 }
@@ -99,12 +106,12 @@ __device__ __noinline__ SC m_sinhcosh(double y)
 }
 #define k_sin(x) m_sincos((x), 0)
 #define k_cos(x) m_sincos((x), 1)
-#define k_tan(x) u_real(CL_TAN, (x), 0.0)
+#define k_tan(x) m_tan(x)
 #define k_exp(x) m_exp(x)
 #define k_log(x) m_log(x)
-#define k_asin(x) u_real(CL_ASIN, (x), 0.0)
-#define k_acos(x) u_real(CL_ACOS, (x), 0.0)
-#define k_pow(x, y) u_real(CL_POWC, (x), (y))
+#define k_asin(x) m_asin(x)
+#define k_acos(x) m_acos(x)
+#define k_pow(x, y) m_pow((x), (y))
 #define k_recip(x) m_recip(x)
 #define k_sqrt(x) m_sqrt(x)
 __device__ __noinline__ double k_hypot(double x, double y) { return hypot(x, y); }
@@ -489,14 +496,14 @@ __device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const dou
         }
         case CL_POWC: {
             const double c = sconst[b];
-            if (acc.im == 0.0 && acc.re > 0.0 && !is_inf(acc.re) && !nonfinite(c) && c != 0.0) { acc.re = u_real(CL_POWC, acc.re, c); break; }
+            if (acc.im == 0.0 && acc.re > 0.0 && !is_inf(acc.re) && !nonfinite(c) && c != 0.0) { acc.re = m_pow(acc.re, c); break; }
             CLOSYR_ZSET(zpow(acc, zmk(c, 0.0)))
         }
         case CL_EXP: CLOSYR_REAL1(true, t ? *t : m_exp(x_), zexp)
         case CL_LOG: CLOSYR_REAL1(x_ > 0.0, t ? *t : m_log(x_), zlog)
-        case CL_TAN: CLOSYR_REAL1(true, t ? *t : u_real(CL_TAN, x_, 0.0), ztan)
-        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : u_real(CL_ASIN, x_, 0.0), zasin)
-        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : u_real(CL_ACOS, x_, 0.0), zacos)
+        case CL_TAN: CLOSYR_REAL1(true, t ? *t : m_tan(x_), ztan)
+        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : m_asin(x_), zasin)
+        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : m_acos(x_), zacos)
         case CL_ABS: CLOSYR_REAL1(true, fabs(x_), zabs)
         default: {
             // slot instructions: `a` is the slot for both the generic and the register forms
@@ -554,7 +561,11 @@ __device__ __forceinline__ R4 k1_unary(uint32_t op, D4 in, double c)
     case CL_COS: CLOSYR_K4(m_sincos(a[j], 1)) break;
     case CL_RECIP: CLOSYR_K4(m_recip(a[j])) break;
     case CL_SQRT: CLOSYR_K4(m_sqrt(a[j])) break;
-    default: CLOSYR_K4(u_real(op, a[j], c)) break;
+    case CL_TAN: CLOSYR_K4(m_tan(a[j])) break;
+    case CL_ASIN: CLOSYR_K4(m_asin(a[j])) break;
+    case CL_ACOS: CLOSYR_K4(m_acos(a[j])) break;
+    case CL_POWC: CLOSYR_K4(m_pow(a[j], c)) break;
+    default: CLOSYR_K4(u_real(op, a[j], c)) break;        // RSQRT POWI ABS
     }
 #undef CLOSYR_K4
     uint32_t ev = 0;
