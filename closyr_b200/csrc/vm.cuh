@@ -304,7 +304,7 @@ __device__ __noinline__ Z ztan(Z a)
 
 __device__ __forceinline__ Z zmul_i(Z a) { return zmk(-a.im, a.re); }
 __device__ __forceinline__ Z zmul_minus_i(Z a) { return zmk(a.im, -a.re); }
-__device__ __forceinline__ Z zsqrt1z(Z z) { return zsqrt(zadd(zv(1.0, 0.0), zneg(zmul(z, z)))); }
+__device__ __forceinline__ Z zsqrt1z(Z z) { return zsqrt(lean_add(zv(1.0, 0.0), zneg(lean_mul(z, z)))); }
 
 __device__ __noinline__ Z zasin(Z a)
 {
@@ -318,7 +318,7 @@ __device__ __noinline__ Z zasin(Z a)
         const double ax = fabs(a.re), l = k_log(ax + sqrt((ax - 1.0) * (ax + 1.0)));
         return a.re > 0.0 ? zmk(3.141592653589793 / 2.0, -l) : zmk(-(3.141592653589793 / 2.0), l);
     }
-    Z w = zlog(zadd(zsqrt1z(a), zmul_i(a)));
+    Z w = zlog(lean_add(zsqrt1z(a), zmul_i(a)));
     int tw = ztag(w);
     if (tw == T_INDET) return zindet();
     if (tw == T_CINF || (tw == T_REAL && isinf(w.re))) return zcinf();
@@ -340,7 +340,7 @@ __device__ __noinline__ Z zacos(Z a)
     int ts = ztag(s);
     if (ts == T_INDET) return zindet();
     if (ts == T_CINF || (ts == T_REAL && isinf(s.re))) return zcinf();
-    Z w = zlog(zadd(a, zmul_i(s)));
+    Z w = zlog(lean_add(a, zmul_i(s)));
     int tw = ztag(w);
     if (tw == T_INDET) return zindet();
     if (tw == T_CINF || (tw == T_REAL && isinf(w.re))) return zcinf();
