@@ -362,8 +362,8 @@ __device__ __noinline__ Z zpowi(Z a, int n)
     int top = 31 - __clz((int)m);
     Z r = a;
     for (int b = top - 1; b >= 0; b--) {
-        r = zmul(r, r);
-        if ((m >> b) & 1u) r = zmul(r, a);
+        r = lean_mul(r, r);
+        if ((m >> b) & 1u) r = lean_mul(r, a);
     }
     if (n < 0) r = zrecip(r);
     return r;
@@ -418,7 +418,7 @@ __device__ __noinline__ Z zpow(Z z, Z w)
         if (az == 1.0) return zindet();
         return ((az > 1.0) == (yr > 0.0)) ? zcinf() : zv(0.0, 0.0);
     }
-    return zexp(zmul(w, zlog(z)));
+    return zexp(lean_mul(w, zlog(z)));
 }
 
 // One point through the program with the complete algebra: only the points the fast path reported come
