@@ -271,7 +271,7 @@ __device__ __noinline__ Z zlog(Z a)
     return zmk(k_log(k_hypot(a.re, a.im)), k_atan2(a.im, a.re));
 }
 
-__device__ __noinline__ Z zsin(Z a)
+__device__ __forceinline__ Z zsin(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
@@ -280,7 +280,7 @@ __device__ __noinline__ Z zsin(Z a)
     return zmk(sc.s * h.c, sc.c * h.s);
 }
 
-__device__ __noinline__ Z zcos(Z a)
+__device__ __forceinline__ Z zcos(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
