@@ -53,3 +53,51 @@ def test_isa_constants_match_header():
         if name == "CL_NUM_OPCODES":
             continue
         assert OPNAMES[int(val)].startswith(name[3:].rstrip("0")[:3]) or OPNAMES[int(val)] == name[3:], (name, val)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: the header must compile as C11 (no C++-isms), and a C program that uses the host-side
+    entry points (builder, text front-end, GA driver; nothing that needs a GPU) must link and run."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "closyr_b200.h"
+int main(void) {
+    closyr_builder *b = 0;
+    closyr_population view;
+    int32_t leafs = 0;
+    char *ff = 0;
+    if (closyr_builder_create(0, &b) != CLOSYR_OK) return 1;
+    if (closyr_builder_add(b, "x*x-1/2") != CLOSYR_OK) return 2;
+    if (closyr_builder_add(b, "Plus(((") == CLOSYR_OK) return 3;              /* parse errors are reported */
+    if (closyr_builder_view(b, &view) != CLOSYR_OK || view.n_expr != 1) return 4;
+    if ((view.meta[0] & 0xffffu) != 7u) return 5;                              /* leafCount of -1/2+x^2 */
+    if (closyr_leaf_count("x*x-1/2", &leafs) != CLOSYR_OK || leafs != 7) return 6;
+    if (closyr_to_fullform("x*x-1/2", &ff) != CLOSYR_OK || strcmp(ff, "Plus(Rational(-1,2),Power(x,2))") != 0) return 7;
+    closyr_free(ff);
+    closyr_builder_destroy(b);
+    int32_t r[2];
+    if (closyr_jrandom_rand_ints(1, 50, 2, r) != CLOSYR_OK || r[0] != 36 || r[1] != 5) return 8;   /* util_prng_test.clj */
+    if (closyr_mutation_count() != 96) return 9;
+    closyr_ctx *ctx = 0;
+    int dev = 0;
+    int rc = closyr_ctx_create(&dev, 1, 0, &ctx);
+    printf("ctx_create rc=%d\n", rc);                                           /* CLOSYR_E_NO_GPU without a device */
+    if (rc == CLOSYR_OK) closyr_ctx_destroy(ctx);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_smoke"
+    inc = os.path.join(ROOT, "include")
+    so_dir = os.path.dirname(L.SO_PATH)
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe),
+                    "-L", so_dir, "-lclosyr_b200", "-Wl,-rpath," + so_dir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "ctx_create rc=" in out.stdout
