@@ -49,6 +49,7 @@ EXPORTS = [
     "closyr_score_batch", "closyr_upload_population", "closyr_score_resident", "closyr_download_scores",
     "closyr_eval_batch", "closyr_score_from_values", "closyr_rank_resident", "closyr_score_partials_resident", "closyr_finalize_partials",
     "closyr_l2_flush", "closyr_fp64_peak_probe", "closyr_kernel_launch_count", "closyr_host_alloc", "closyr_host_free",
+    "closyr_selftest_pinned_fallback",
     "closyr_builder_create", "closyr_builder_destroy", "closyr_builder_clear", "closyr_builder_add",
     "closyr_builder_add_many", "closyr_builder_view", "closyr_to_fullform", "closyr_leaf_count", "closyr_free",
     "closyr_generate_population",

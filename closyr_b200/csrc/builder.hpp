@@ -12,26 +12,42 @@
 namespace closyr {
 
 // growable host buffer, optionally page-locked so the H2D copy of a generation is a single DMA
+// `alloc_pinned` / `free_pinned` are replaceable so that a test can make the page-locked allocator fail.
 template <typename T> struct Buf {
     T *p = nullptr;
     size_t n = 0, cap = 0;
-    bool pinned = false;
+    bool pinned = false;          // page-locked memory is wanted for the next allocation
+    bool p_is_pinned = false;     // how the CURRENT block was allocated (decides how it is released)
+    void *(*alloc_pinned)(size_t) = pinned_alloc;
+    void (*free_pinned)(void *) = pinned_free;
     ~Buf() { release(); }
+    void release_block(T *q, bool was_pinned)
+    {
+        if (!q) return;
+        if (was_pinned) free_pinned(q);
+        else free(q);
+    }
     void release()
     {
-        if (p) { if (pinned) pinned_free(p); else free(p); }
-        p = nullptr; n = cap = 0;
+        release_block(p, p_is_pinned);
+        p = nullptr; n = cap = 0; p_is_pinned = false;
     }
     bool reserve(size_t want)
     {
         if (want <= cap) return true;
         size_t nc = cap ? cap : 1024;
         while (nc < want) nc *= 2;
-        T *q = pinned ? (T *)pinned_alloc(nc * sizeof(T)) : (T *)malloc(nc * sizeof(T));
-        if (!q && pinned) { pinned = false; q = (T *)malloc(nc * sizeof(T)); }   // no CUDA driver: pageable
+        bool q_pinned = pinned;
+        T *q = pinned ? (T *)alloc_pinned(nc * sizeof(T)) : (T *)malloc(nc * sizeof(T));
+        if (!q && pinned) {                        // no CUDA driver, or the page-lock limit is reached: pageable
+            pinned = false;
+            q_pinned = false;
+            q = (T *)malloc(nc * sizeof(T));
+        }
         if (!q) return false;
-        if (p) { memcpy(q, p, n * sizeof(T)); if (pinned) pinned_free(p); else free(p); }
-        p = q; cap = nc;
+        if (p) memcpy(q, p, n * sizeof(T));
+        release_block(p, p_is_pinned);             // the OLD block goes back to the allocator it came from
+        p = q; cap = nc; p_is_pinned = q_pinned;
         return true;
     }
     bool append(const T *src, size_t k)

@@ -131,9 +131,23 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     dp.const_base = pop->const_off[lo];
     const size_t ncode = pop->code_off[hi] - dp.code_base, nk = pop->const_off[hi] - dp.const_base;
     uint32_t mc = 0, mk = 0;
+    // the layout the kernel's TMA staging depends on (include/closyr_b200.h): every program starts on a 16-byte
+    // boundary and is a whole number of 16-byte units; offsets never decrease.  A violation would be a misaligned
+    // bulk copy (sticky context error) or a wrapped size, so it is refused here.
+    if (pop->code_off[hi] % 4u != 0 || pop->const_off[hi] % 2u != 0)
+        return fail(ctx, CLOSYR_E_ARG, "population layout: code_off must be a multiple of 4 words, const_off of 2 doubles");
     for (int64_t e = lo; e < hi; e++) {
-        mc = std::max(mc, pop->code_off[e + 1] - pop->code_off[e]);
-        mk = std::max(mk, pop->const_off[e + 1] - pop->const_off[e]);
+        const uint32_t c0 = pop->code_off[e], c1 = pop->code_off[e + 1], k0 = pop->const_off[e], k1 = pop->const_off[e + 1];
+        if (c0 % 4u != 0 || k0 % 2u != 0)
+            return fail(ctx, CLOSYR_E_ARG, "population layout: code_off must be a multiple of 4 words, const_off of 2 doubles (expression " + std::to_string(e) + ")");
+        if (c1 < c0 || k1 < k0)
+            return fail(ctx, CLOSYR_E_ARG, "population layout: offsets must not decrease (expression " + std::to_string(e) + ")");
+        if (c1 == c0)
+            return fail(ctx, CLOSYR_E_ARG, "population layout: empty program (expression " + std::to_string(e) + "); a program ends with CL_END");
+        if ((pop->code[c1 - 1] & 0xffu) != CL_END)
+            return fail(ctx, CLOSYR_E_ARG, "population layout: program does not end with CL_END (expression " + std::to_string(e) + ")");
+        mc = std::max(mc, c1 - c0);
+        mk = std::max(mk, k1 - k0);
     }
     if (mc > CLOSYR_MAX_CODE_WORDS || mk > CLOSYR_MAX_CONSTS)
         return fail(ctx, CLOSYR_E_ARG, "population holds a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS");
@@ -294,7 +308,7 @@ void closyr_ctx_destroy(closyr_ctx *ctx)
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        for (DevBuf *b : { &d.xs, &d.ys, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
+        for (DevBuf *b : { &d.xs, &d.ys, &d.leaf_tab, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
                            &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b })
             b->release();
         d.pop.release();
@@ -314,16 +328,23 @@ int closyr_set_points(closyr_ctx *ctx, const double *xs, const double *ys, int64
     if (!ctx || n < 0 || (n > 0 && (!xs || !ys))) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_set_points");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->err.clear();
+    const std::vector<double> ones(CHUNK_POINTS, 1.0);      // alive until the streams are synchronised below
     for (auto &d : ctx->devs) {
         CU(ctx, cudaSetDevice(d.device));
-        CU(ctx, d.xs.reserve((size_t)n * 8 + 64));
-        CU(ctx, d.ys.reserve((size_t)n * 8 + 64));
+        // padded to whole 128-point chunks (x = 1.0, y = 0.0) so that a lane always loads its 4 points
+        const int64_t padded = n_chunks_of(n) * CHUNK_POINTS;
+        CU(ctx, d.xs.reserve((size_t)padded * 8 + 64));
+        CU(ctx, d.ys.reserve((size_t)padded * 8 + 64));
         if (n) {
             CU(ctx, cudaMemcpyAsync(d.xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
             CU(ctx, cudaMemcpyAsync(d.ys.p, ys, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+            if (padded > n) {
+                CU(ctx, cudaMemcpyAsync((double *)d.xs.p + n, ones.data(), (size_t)(padded - n) * 8, cudaMemcpyHostToDevice, d.stream));
+                CU(ctx, cudaMemsetAsync((double *)d.ys.p + n, 0, (size_t)(padded - n) * 8, d.stream));
+            }
         }
         // f(x_i) tables of the raw variable, shared by every expression of every generation scored on these points
-        d.leaf_stride = n_chunks_of(n) * CHUNK_POINTS;
+        d.leaf_stride = padded;
         if (d.leaf_stride > 0) {
             CU(ctx, d.leaf_tab.reserve((size_t)d.leaf_stride * LEAF_TAB_ROWS * 8));
             launch_leaf_table((const double *)d.xs.p, n, d.leaf_stride, (double *)d.leaf_tab.p, d.stream);
@@ -512,10 +533,13 @@ int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const doubl
     if (ne == 0) return CLOSYR_OK;
     rc = upload_shard(ctx, d, d.eval_pop, pop, 0, ne);
     if (rc) return rc;
-    CU(ctx, d.eval_xs.reserve((size_t)n * 8 + 64));
+    const int64_t padded = n_chunks_of(n) * CHUNK_POINTS;      // whole chunks, x = 1.0 beyond n (as closyr_set_points)
+    const std::vector<double> ones(CHUNK_POINTS, 1.0);
+    CU(ctx, d.eval_xs.reserve((size_t)padded * 8 + 64));
     CU(ctx, d.eval_f.reserve((size_t)std::max<int64_t>(1, ne * n) * 8));
     CU(ctx, d.eval_status.reserve((size_t)ne));
     if (n) CU(ctx, cudaMemcpyAsync(d.eval_xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+    if (padded > n) CU(ctx, cudaMemcpyAsync((double *)d.eval_xs.p + n, ones.data(), (size_t)(padded - n) * 8, cudaMemcpyHostToDevice, d.stream));
     EvalParams ep;
     ep.pop = d.eval_pop.view();
     ep.xs = (const double *)d.eval_xs.p;

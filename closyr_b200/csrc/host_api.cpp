@@ -26,7 +26,33 @@ void set_error(const std::string &s) { g_last_error = s; }
 
 extern "C" {
 
-const char *closyr_version(void) { return "closyr_b200 0.1 (ISA v1, sm_100a)"; }
+const char *closyr_version(void) { return "closyr_b200 0.2 (ISA v1.1, sm_100a)"; }
+
+// ---- self test of the builder's buffer (tests/test_abi.py): the page-locked allocator fails on the second growth; the
+// block allocated first must go back to the page-locked deallocator, the data must survive, later blocks are pageable
+namespace {
+int g_fake_pinned_allocs = 0, g_fake_pinned_frees = 0;
+void *fake_pinned_alloc(size_t bytes) { return ++g_fake_pinned_allocs == 1 ? malloc(bytes) : nullptr; }
+void fake_pinned_free(void *p) { g_fake_pinned_frees++; free(p); }
+}  // namespace
+
+int closyr_selftest_pinned_fallback(void)
+{
+    g_fake_pinned_allocs = g_fake_pinned_frees = 0;
+    {
+        closyr::Buf<uint32_t> b;
+        b.pinned = true;
+        b.alloc_pinned = fake_pinned_alloc;
+        b.free_pinned = fake_pinned_free;
+        for (uint32_t i = 0; i < 5000; i++)
+            if (!b.push(i * 7u)) return -1;
+        if (g_fake_pinned_allocs != 2 || g_fake_pinned_frees != 1) return -2;      // first block pinned, freed as pinned
+        if (b.pinned || b.p_is_pinned) return -3;                                   // the current block is pageable
+        for (uint32_t i = 0; i < 5000; i++)
+            if (b.p[i] != i * 7u) return -4;
+    }
+    return g_fake_pinned_frees == 1 ? 0 : -5;                                       // the destructor used free()
+}
 
 int closyr_builder_create(uint32_t flags, closyr_builder **out)
 {

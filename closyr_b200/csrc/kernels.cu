@@ -10,6 +10,7 @@
 // closyr's formula operation by operation (reference src/closyr/ops.clj:78-116); the file is compiled with
 // -fmad=false so none of it is contracted.
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "vm.cuh"
@@ -48,54 +49,92 @@ __device__ __forceinline__ double score_formula(double sum, double mx, int64_t n
 }
 
 struct Staged {
-    const uint32_t *scode;
     const double *sconst;
-    double *slvl;      // per-chunk sums of the tile (score_kernel) / scratch
-    double *sslot;     // this lane's column of the warp's spill slots: [slot 0..3][point 0..3][lane]
+    double *slvl;              // per-chunk sums of the tile (score_kernel) / scratch
+    uint32_t tcode_addr;       // shared-window address of the threaded code (vm.cuh)
+    uint32_t slot_addr;        // shared-window address of this lane's column of the warp's spill slots
+    uint32_t pflags;           // PF_* properties of the program
     const double *leaf_tab;    // f(x_i) tables of the resident points (ScoreParams), nullptr when xs are ad hoc
-    int64_t leaf_stride;
 };
 
 constexpr int SLOT_DOUBLES_PER_WARP = CLOSYR_REG_SLOTS * POINTS_PER_LANE * 32;
 
-// copies one program into shared memory: [warp slots | constants | `nlvl` doubles of scratch | code (+1 word)]
+// shared memory of a CTA: [warp slots | constants | `nlvl` doubles of scratch | threaded code (ncode + 1 entries) |
+// the program as the caller wrote it (ncode words)]
+struct SmemLayout {
+    double *sconst, *slvl;
+    TInsn *tcode;
+    uint32_t *raw;
+};
+__device__ __forceinline__ SmemLayout smem_layout(unsigned char *smem, int nthreads, uint32_t nk, int nlvl, uint32_t ncode)
+{
+    SmemLayout L;
+    L.sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
+    L.slvl = L.sconst + ((nk + 1) & ~1u);
+    L.tcode = reinterpret_cast<TInsn *>(L.slvl + ((nlvl + 1) & ~1));      // 16-byte aligned
+    L.raw = reinterpret_cast<uint32_t *>(L.tcode + ncode + 1);
+    return L;
+}
+
+// translates the staged program into threaded code (one entry per word, one word per thread and pass) and collects
+// the program's properties; every thread of the CTA calls it after the program and its constants are visible
+__device__ __forceinline__ Staged finish_stage(const SmemLayout &L, uint32_t ncode, unsigned char *smem, int tid, int nthreads,
+                                               const double *leaf_tab, int64_t leaf_stride, uint32_t *s_pflags)
+{
+    uint32_t pf = 0;
+    for (uint32_t i = tid; i <= ncode; i += nthreads) {      // entry `ncode` is the slack the prefetch reads
+        TInsn t;
+        pf |= decode_insn(i < ncode ? L.raw[i] : 0u, L.sconst, leaf_tab != nullptr, leaf_stride, t);
+        L.tcode[i] = t;
+    }
+    if (pf) atomicOr(s_pflags, pf);
+    __syncthreads();
+    Staged st;
+    st.sconst = L.sconst;
+    st.slvl = L.slvl;
+    st.tcode_addr = (uint32_t)__cvta_generic_to_shared(L.tcode);
+    st.slot_addr = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31));
+    st.pflags = *s_pflags;
+    st.leaf_tab = leaf_tab;
+    return st;
+}
+
+// copies one program into shared memory with plain loads (eval_kernel: one warp per expression)
 __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
-                                                int nthreads, int nlvl)
+                                                int nthreads, int nlvl, uint32_t *s_pflags)
 {
     const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
     const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
     const uint32_t ncode = c1 - c0, nk = k1 - k0;
-    double *sslot = reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31);
-    double *sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
-    double *slvl = sconst + nk;
-    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + nlvl);
+    const SmemLayout L = smem_layout(smem, nthreads, nk, nlvl, ncode);
     const double *gk = pop.consts + (k0 - pop.const_base);
     const uint32_t *gc = pop.code + (c0 - pop.code_base);
-    for (uint32_t i = tid; i < nk; i += nthreads) sconst[i] = gk[i];
-    for (uint32_t i = tid; i < ncode; i += nthreads) scode[i] = gc[i];
-    if (tid == 0) scode[ncode] = 0;
-    Staged s = { scode, sconst, slvl, sslot, nullptr, 0 };
-    return s;
+    for (uint32_t i = tid; i < nk; i += nthreads) L.sconst[i] = gk[i];
+    for (uint32_t i = tid; i < ncode; i += nthreads) L.raw[i] = gc[i];
+    if (tid == 0) *s_pflags = 0;
+    __syncthreads();
+    return finish_stage(L, ncode, smem, tid, nthreads, nullptr, 0, s_pflags);
 }
 
 // One round of a CTA = one 128-point chunk per warp: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points
 // whose value is not a real number (eval.clj:70-80 turns those into +Inf).
 //
 // Every warp first runs the IEEE-real fast path on its chunk.  The points it reports are compacted across
-// the WHOLE CTA into one list and re-evaluated with the complete algebra by all threads, one point per thread
-// per pass -- so the extra work of a chunk that left the real line is shared by the 32 warps instead of
-// stalling the CTA behind one warp.  `mode` is the CTA's adaptive state: when most points of the previous
-// round needed the complete algebra the fast pass is skipped.  Both evaluators give bit-identical values
-// wherever the fast path is valid, so the heuristic cannot change a score.
+// the WHOLE CTA into one list and re-evaluated with the complete algebra, 64 points (2 per lane) per warp and
+// pass -- so the extra work of a chunk that left the real line is shared by all warps instead of stalling the
+// CTA behind one of them.  `mode` is the CTA's adaptive state: when most points of the previous round needed
+// the complete algebra the fast pass is skipped.  Both evaluators give bit-identical values wherever the fast
+// path is valid, so the heuristic cannot change a score.
 // Must be called by every thread of the CTA (it contains __syncthreads).
 struct Round {
     double *list;          // [warps * 128] indices of the reported points, replaced in place by their results
     uint32_t *counts;      // [2][32] reported points per warp, double-buffered by round parity
 };
+constexpr int CPLX_POINTS = 2;       // points per lane of the complete-algebra interpreter
 
 __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bool active, bool is_const, bool quirk,
                                            uint32_t quirk_off, int64_t base, int64_t n, const double *__restrict__ xs,
-                                           double (&x)[4], double (&v)[4], uint32_t &valid, uint32_t &nr, uint32_t &mode,
+                                           double (&v)[4], uint32_t &valid, uint32_t &nr, uint32_t &mode,
                                            uint32_t round_parity)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -103,32 +142,22 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
     nr = 0;
     uint32_t ev = 0;
     if (active) {
-        if (base + 3 < n) {
-            const double2 a = *reinterpret_cast<const double2 *>(xs + base);
-            const double2 b = *reinterpret_cast<const double2 *>(xs + base + 2);
-            x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
-            valid = 0xfu;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool ok = base + j < n;
-                x[j] = ok ? xs[base + j] : 1.0;
-                valid |= (ok ? 1u : 0u) << j;
-            }
-        }
+        // xs (and every table row) is padded to whole chunks with x = 1.0, so a lane always loads its 4 points
+        const int64_t left = n - base;
+        valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
         if (quirk) {
             // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
 #pragma unroll
             for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
-        } else if (mode == 0 && !is_const) {
-            ev = run_real<4>(st.scode, st.sconst, st.sslot, x, v, st.leaf_tab ? st.leaf_tab + base : nullptr, st.leaf_stride) & valid;
-            // a NaN that no instruction reported is Indeterminate in the full algebra: never a real number
+        } else if (mode == 0 && !is_const && !(st.pflags & PF_NO_FAST)) {
+            const RealResult<4> rr = run_real<4>(st.tcode_addr, st.slot_addr, xs + base, st.leaf_tab ? st.leaf_tab + base : nullptr);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (v[j] != v[j] && !((ev >> j) & 1u)) { v[j] = 0.0; nr |= 1u << j; }
-            nr &= valid;
+            for (int j = 0; j < 4; j++) v[j] = rr.v[j];
+            ev = rr.ev & valid;
         } else ev = valid;
     }
+    // nothing reported anywhere in the CTA (the common round): one barrier, no compaction
+    if (!__syncthreads_or(ev != 0)) return false;
     // CTA-wide compaction of the reported points
     const uint32_t mine = __popc(ev);
     uint32_t incl = mine;
@@ -147,17 +176,26 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
         if (lane >= d) ci += t;
     }
     const uint32_t total = __shfl_sync(FULL, ci, 31);
-    if (total == 0) return false;
     uint32_t pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
 #pragma unroll
     for (int j = 0; j < 4; j++)
         if ((ev >> j) & 1u) rd.list[pos++] = __longlong_as_double(base + j);      // the point's index
     __syncthreads();
-    for (uint32_t r = tid; r < total; r += blockDim.x) {
-        const int64_t idx = __double_as_longlong(rd.list[r]);
-        const Z z = run_full(st.scode, st.sconst, xs[idx], st.leaf_tab ? st.leaf_tab + idx : nullptr, st.leaf_stride);
-        const bool real = z.re == z.re && z.im == 0.0;
-        rd.list[r] = real ? z.re : __longlong_as_double(0x7ff8000000000000ll);    // NaN marks "not a real number"
+    constexpr uint32_t TASK = 32 * CPLX_POINTS;
+    for (uint32_t t0 = warp * TASK; t0 < total; t0 += nwarps * TASK) {
+        CplxArgs<CPLX_POINTS> ca;
+#pragma unroll
+        for (int j = 0; j < CPLX_POINTS; j++) {
+            const uint32_t r = t0 + j * 32 + lane;
+            ca.idx[j] = __double_as_longlong(rd.list[r < total ? r : t0]);       // idle lanes repeat the task's first point
+        }
+        const CplxResult<CPLX_POINTS> cr = run_cplx<CPLX_POINTS>(st.tcode_addr, st.slot_addr, st.sconst, xs, ca, st.leaf_tab);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < CPLX_POINTS; j++) {
+            const uint32_t r = t0 + j * 32 + lane;
+            if (r < total) rd.list[r] = ((cr.nonreal >> j) & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : cr.out[j];   // NaN marks "not a real number"
+        }
     }
     __syncthreads();
     pos -= mine;
@@ -166,7 +204,7 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
         if ((ev >> j) & 1u) {
             const double r = rd.list[pos++];
             if (r != r) { v[j] = 0.0; nr |= 1u << j; }
-            else { v[j] = r; nr &= ~(1u << j); }
+            else v[j] = r;
         }
     }
     mode = (total * 4u >= (uint32_t)blockDim.x * 4u * 3u) ? 1u : 0u;      // >= 75 % of the round's points
@@ -202,29 +240,27 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// stages one program with two TMA bulk copies ([warp slots | constants | scratch | code]); every thread of the
-// CTA calls it, thread 0 issues the copies and everybody waits on the mbarrier (single use: parity 0)
+// stages one program with two TMA bulk copies and translates it; every thread of the CTA calls it, thread 0 issues
+// the copies and everybody waits on the mbarrier (single use: parity 0)
 __device__ __forceinline__ Staged stage_program_tma(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
-                                                    int nthreads, int nlvl, unsigned long long *bar)
+                                                    int nthreads, int nlvl, unsigned long long *bar, const double *leaf_tab,
+                                                    int64_t leaf_stride, uint32_t *s_pflags)
 {
     const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
     const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
     const uint32_t ncode = c1 - c0, nk = k1 - k0;
-    double *sslot = reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31);
-    double *sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
-    double *slvl = sconst + nk;
-    uint32_t *scode = reinterpret_cast<uint32_t *>(slvl + ((nlvl + 1) & ~1));      // 16-byte aligned
+    const SmemLayout L = smem_layout(smem, nthreads, nk, nlvl, ncode);
     if (tid == 0) {
+        *s_pflags = 0;
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar, ncode * 4u + nk * 8u);
-        if (nk) bulk_g2s(sconst, pop.consts + (k0 - pop.const_base), nk * 8u, bar);
-        bulk_g2s(scode, pop.code + (c0 - pop.code_base), ncode * 4u, bar);
+        if (nk) bulk_g2s(L.sconst, pop.consts + (k0 - pop.const_base), nk * 8u, bar);
+        bulk_g2s(L.raw, pop.code + (c0 - pop.code_base), ncode * 4u, bar);
     }
     __syncthreads();                 // the initialised barrier is visible to every waiter
     mbar_wait(bar, 0);
-    Staged s = { scode, sconst, slvl, sslot, nullptr, 0 };
-    return s;
+    return finish_stage(L, ncode, smem, tid, nthreads, leaf_tab, leaf_stride, s_pflags);
 }
 
 __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
@@ -256,9 +292,9 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     }
 
     __shared__ __align__(8) unsigned long long s_bar;
-    Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS, &s_bar);
-    st.leaf_tab = p.leaf_tab;
-    st.leaf_stride = p.leaf_stride;
+    __shared__ uint32_t s_pflags;
+    const Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS,
+                                        &s_bar, p.leaf_tab, p.leaf_stride, &s_pflags);
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -278,17 +314,14 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         const int64_t c = c0 + warp;
         const bool active = c < c_hi;
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        double x[4], v[4], y[4];
+        double v[4], y[4];
         uint32_t valid, nr;
-        used_full |= eval_round(st, rd, active, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode, parity);
+        used_full |= eval_round(st, rd, active, is_const, quirk, quirk_off, base, p.n, p.xs, v, valid, nr, mode, parity);
         if (!active) continue;
-        if (base + 3 < p.n) {
+        {                                                      // ys is padded to whole chunks like xs
             const double2 a = *reinterpret_cast<const double2 *>(p.ys + base);
             const double2 b = *reinterpret_cast<const double2 *>(p.ys + base + 2);
             y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) y[j] = (base + j < p.n) ? p.ys[base + j] : 0.0;
         }
         // compute-residual (ops.clj:78-90): NaN or non-real => max-resid; else min(max-resid, |y - f|)
         double s = 0.0, m = 0.0;
@@ -400,8 +433,8 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
         if (lane == 0) p.status[e] = 1;
         return;
     }
-    const Staged st = stage_program(p.pop, e, smem, lane, 32, CHUNK_POINTS);
-    __syncwarp();
+    __shared__ uint32_t s_pflags;
+    const Staged st = stage_program(p.pop, e, smem, lane, 32, CHUNK_POINTS, &s_pflags);
     const bool is_const = (flags & CL_F_CONST) != 0;
     const uint32_t aux = p.pop.aux[e];
     const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
@@ -413,9 +446,9 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t c = 0; c < nchunks; c++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        double x[4], v[4];
+        double v[4];
         uint32_t valid, nr;
-        eval_round(st, rd, true, is_const, quirk, quirk_off, base, p.n, p.xs, x, v, valid, nr, mode, (uint32_t)(c & 1));
+        eval_round(st, rd, true, is_const, quirk, quirk_off, base, p.n, p.xs, v, valid, nr, mode, (uint32_t)(c & 1));
         nonreal += __popc(nr);
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -483,8 +516,8 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters)
     out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// f(x_i) for the parameter-free elementary functions of the raw variable, through the very routine the
-// interpreter's fast path calls (k1_unary), so a table entry is bit-identical to computing it in score_kernel.
+// f(x_i) for the parameter-free elementary functions of the raw variable, through the very routines the
+// interpreters use (f_tabulated), so a table entry is bit-identical to computing it in score_kernel.
 // Entries past n (the table is padded to whole chunks) take x = 1.0, as the kernel does for absent points.
 __global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restrict__ xs, int64_t n, int64_t stride,
                                                            double *__restrict__ tab)
@@ -492,14 +525,15 @@ __global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restric
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i0 = q * 4;
     if (i0 >= stride) return;
-    D4 in;
+    double in[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) in.v[j] = (i0 + j < n) ? xs[i0 + j] : 1.0;
+    for (int j = 0; j < 4; j++) in[j] = (i0 + j < n) ? xs[i0 + j] : 1.0;
     for (uint32_t op = CL_RECIP; op <= CL_ACOS; op++) {
         if (!((LEAF_TAB_MASK >> (op - CL_RECIP)) & 1u)) continue;
-        const R4 r = k1_unary(op, in, 0.0);
+        double a[4] = { in[0], in[1], in[2], in[3] };
+        f_tabulated<4>(op, a);
 #pragma unroll
-        for (int j = 0; j < 4; j++) tab[(int64_t)(op - CL_RECIP) * stride + i0 + j] = r.d.v[j];
+        for (int j = 0; j < 4; j++) tab[(int64_t)(op - CL_RECIP) * stride + i0 + j] = a[j];
     }
 }
 
@@ -551,14 +585,21 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
 
 size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps)
 {
-    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)max_consts * 8 + (size_t)((chunks_per_tile + 1) & ~1) * 8 +
-           (size_t)warps * CHUNK_POINTS * 8 +
-           ((size_t)max_code_words + 1) * 4 + 16;
+    // [warp slots | constants | chunk sums + the compaction list | threaded code | the program]  (smem_layout)
+    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)((max_consts + 1) & ~1u) * 8 +
+           (size_t)((chunks_per_tile + warps * CHUNK_POINTS + 1) & ~1) * 8 +
+           ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + (size_t)max_code_words * 4 + 16;
 }
 int score_warps(int32_t chunks_per_tile)
 {
+    // CLOSYR_SCORE_WARPS (a power of two <= 32) caps the CTA size: a tuning knob for measurements, not an API
+    static const int cap = [] {
+        const char *e = getenv("CLOSYR_SCORE_WARPS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= MAX_SCORE_WARPS && (v & (v - 1)) == 0) ? v : MAX_SCORE_WARPS;
+    }();
     int w = 1;
-    while (w < MAX_SCORE_WARPS && w < chunks_per_tile) w <<= 1;
+    while (w < cap && w < chunks_per_tile) w <<= 1;
     return w;
 }
 

@@ -1,15 +1,22 @@
 // vm.cuh -- device-side bytecode interpreters for sm_100a.
 //
-// Two evaluators share one ISA (include/closyr_b200.h):
-//   * run_real<P>:  the fast path.  IEEE-754 fp64 on P points per lane, accumulator and spill slots 0..3 in
-//                   registers, every lane of the warp runs the same program so the dispatch branch is uniform.
-//                   It is exact whenever the evaluation stays on the real line; it reports (per point) when
-//                   it cannot know that: the result is NaN, or an instruction met a case where Symja's value
-//                   algebra differs observably from IEEE (E^(-Infinity) vs E^ComplexInfinity, literals that are
-//                   not real, general x^y).
-//   * full_eval:    the complete value algebra of the scoring path (reals, complex numbers, ComplexInfinity,
-//                   Indeterminate; SURVEY.md Appendix A, DESIGN.md "Semantics"), one point per lane.  Only the
-//                   128-point chunks in which some point raised the report above are re-evaluated with it.
+// The ISA of include/closyr_b200.h is what the caller writes; a CTA translates the program it staged into
+// THREADED CODE once (decode_program: 16 bytes per instruction = handler index, operand word, the fp64 literal
+// itself) so that the interpreters dispatch with one LDS.128 and one jump-table branch, without modifier tests,
+// slot tests or constant-pool indexing.  Two evaluators run that code:
+//   * run_real<P>:  the fast path.  IEEE-754 fp64 on P points per lane, accumulator in registers, spill slots in
+//                   shared memory, every lane of the warp runs the same program so the dispatch branch is uniform.
+//                   It is exact whenever the evaluation stays on the real line; it reports (per point) when it
+//                   cannot know that: the result is NaN (NaN is absorbing on this path, so a domain exit anywhere
+//                   shows in the result), or an instruction that maps an infinity to a finite number was handed one
+//                   (IEEE cannot tell ComplexInfinity from a directed infinity, nor from an Indeterminate the
+//                   algebra reached earlier).
+//   * run_cplx<PC>: the complete value algebra of the scoring path (reals, complex numbers, ComplexInfinity,
+//                   Indeterminate; SURVEY.md Appendix A, DESIGN.md "Semantics"), PC points per lane over (re, im)
+//                   register pairs.  The warp is in REAL MODE while every value of the accumulator is on the real
+//                   line (same handlers and same arithmetic as run_real) and switches to COMPLEX MODE at the first
+//                   instruction that leaves it; a leaf load switches back.  Special values (infinities,
+//                   Indeterminate) take a per-point scalar path through the z* functions below.
 // What is being replaced: Symja's ExprEvaluator.eval of Function({x},expr)[List(xs)]
 // (reference src/closyr/ops/eval.clj:40-56) and the per-element decode (eval.clj:70-80).
 #pragma once
@@ -53,41 +60,31 @@ __device__ __forceinline__ double powi_real(double a, int n)
 }
 
 
-// scalar entry points of the lean routines (vmath.cuh): a few hundred bytes each, shared by both evaluators
+// scalar entry points of the lean routines (vmath.cuh): a few hundred bytes each, used by the complex algebra
 __device__ __noinline__ double m_exp(double x) { double t[1] = { x }; v_exp<1>(t); return t[0]; }
 __device__ __noinline__ double m_log(double x) { double t[1] = { x }; v_log<1>(t); return t[0]; }
-__device__ __noinline__ double m_sincos(double x, int shift) { double t[1] = { x }; v_sincos<1>(t, shift); return t[0]; }
+__device__ __noinline__ double m_sin(double x) { double t[1] = { x }; v_sin<1>(t); return t[0]; }
+__device__ __noinline__ double m_cos(double x) { double t[1] = { x }; v_cos<1>(t); return t[0]; }
 struct SC { double s, c; };
-__device__ __noinline__ SC m_sincos_both(double x) { SC r; v_sincos_both(x, r.s, r.c); return r; }
-__device__ __noinline__ double m_recip(double x) { return 1.0 / x; }
-__device__ __noinline__ double m_sqrt(double x) { return sqrt(x); }
+__device__ __noinline__ SC m_sincos_both(double x)
+{
+    double s[1] = { x }, c[1] = { x };
+    v_sin<1>(s);
+    v_cos<1>(c);
+    SC r;
+    r.s = s[0];
+    r.c = c[0];
+    return r;
+}
+__device__ __forceinline__ double m_recip(double x) { return 1.0 / x; }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
 
-// the library routines that have no lean version: one copy each, called directly by both evaluators
+// the library routines that have no lean version: one copy each, called by both evaluators
 __device__ __noinline__ double m_tan(double x) { return tan(x); }
 __device__ __noinline__ double m_asin(double x) { return asin(x); }
 __device__ __noinline__ double m_acos(double x) { return acos(x); }
 __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
 
-// real elementary function `op` of a (c = the literal operand of POWI / POWC): the generic entry, used where the
-// operation is not known at compile time
-__device__ __noinline__ double u_real(uint32_t op, double a, double c)
-{
-    switch (op) {
-    case CL_RECIP: return m_recip(a);
-    case CL_SQRT: return m_sqrt(a);
-    case CL_RSQRT: return m_recip(m_sqrt(a));
-    case CL_POWI: return powi_real(a, (int)c);
-    case CL_POWC: return m_pow(a, c);
-    case CL_EXP: return m_exp(a);
-    case CL_LOG: return m_log(a);
-    case CL_SIN: return m_sincos(a, 0);
-    case CL_COS: return m_sincos(a, 1);
-    case CL_TAN: return m_tan(a);
-    case CL_ASIN: return m_asin(a);
-    case CL_ACOS: return m_acos(a);
-    default: return fabs(a);            // CL_ABS
-    }
-}
 // sinh and cosh of the same argument (the complex sin / cos / tan need both): one exponential where that is
 // accurate (0.5 <= |y| < 700: e - 1/e cancels at most one bit there), the library routines elsewhere
 __device__ __noinline__ SC m_sinhcosh(double y)
@@ -104,8 +101,8 @@ __device__ __noinline__ SC m_sinhcosh(double y)
     }
     return r;
 }
-#define k_sin(x) m_sincos((x), 0)
-#define k_cos(x) m_sincos((x), 1)
+#define k_sin(x) m_sin(x)
+#define k_cos(x) m_cos(x)
 #define k_tan(x) m_tan(x)
 #define k_exp(x) m_exp(x)
 #define k_log(x) m_log(x)
@@ -202,7 +199,7 @@ __device__ __forceinline__ Z lean_mul(Z a, Z b)         // at least one operand 
     return zmul(a, b);
 }
 
-__device__ __forceinline__ Z zneg(Z a)
+__device__ __noinline__ Z zneg(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET) return zindet();
@@ -271,7 +268,7 @@ __device__ __noinline__ Z zlog(Z a)
     return zmk(k_log(k_hypot(a.re, a.im)), k_atan2(a.im, a.re));
 }
 
-__device__ __forceinline__ Z zsin(Z a)
+__device__ __noinline__ Z zsin(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
@@ -280,7 +277,7 @@ __device__ __forceinline__ Z zsin(Z a)
     return zmk(sc.s * h.c, sc.c * h.s);
 }
 
-__device__ __forceinline__ Z zcos(Z a)
+__device__ __noinline__ Z zcos(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET || t == T_CINF) return zindet();
@@ -347,7 +344,7 @@ __device__ __noinline__ Z zacos(Z a)
     return zmul_minus_i(w);
 }
 
-__device__ __forceinline__ Z zabs(Z a)
+__device__ __noinline__ Z zabs(Z a)
 {
     int t = ztag(a);
     if (t == T_INDET) return zindet();
@@ -421,121 +418,104 @@ __device__ __noinline__ Z zpow(Z z, Z w)
     return zexp(lean_mul(w, zlog(z)));
 }
 
-// One point through the program with the complete algebra: only the points the fast path reported come
-// here.  Flat on purpose -- one switch, the real-line case of every instruction inline (the same IEEE sequence
-// as the fast path, through the same m_* routines), one call into z* only when a value is off the real line.
-// A first version went through one generic per-value routine and then u_real -> m_*: 125 instructions per point-instruction and an
-// instruction-fetch stall at almost every step (ncu profile r01_f).
-#define CLOSYR_ZSET(expr) { acc = (expr); break; }
-#define CLOSYR_REAL1(cond, fast, zf)                        \
-    {                                                       \
-        const double x_ = acc.re;                           \
-        if (acc.im == 0.0 && (cond)) { acc.re = (fast); break; } \
-        CLOSYR_ZSET(zf(acc))                                \
-    }
-// `tab` (or nullptr) points at this point's column of the f(x_i) tables (kernels.cuh): an elementary function of
-// the raw variable takes its value from there whenever it would have called the real routine.
-__device__ __noinline__ Z run_full(const uint32_t *__restrict__ scode, const double *__restrict__ sconst, double x,
-                                   const double *__restrict__ tab, int64_t tab_stride)
+// ------------------------------------------------------------------------------------------------
+// threaded code: what a CTA interprets.  One entry per ISA word (same index), 16 bytes:
+//   h    handler index (TH_*)
+//   aux  leaf loads, TH_TAB, TH_MOD: bit 0 SRCX, bit 1 PUSH, bits 10..11 push slot (= its byte offset, 1 KiB per slot),
+//        bits 2..9 the function's own handler (TH_TAB / TH_MOD); bits 16..31 the ISA `b` field (POWI exponent, LDZ
+//        constant index) or LDSPEC's `a`;  ST / ADDS / MULS / POWS: slot number << 10
+//   c    the fp64 literal of ADDC / MULC / LDC / POWC, or (TH_TAB) the byte offset of the function's table row
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) TInsn { uint32_t h, aux; double c; };
+
+enum {
+    // the "cheap" handlers, 0 .. TH_CHEAP - 1: run_real interprets them inside one PTX block (brx.idx dispatch).
+    // The ...P forms store acc to a slot first (ISA v1.1 PUSH); TH_TAB = a tabulated function of the raw variable
+    // that is real everywhere (sin cos exp tan 1/x)
+    TH_END = 0, TH_LDX, TH_LDXP, TH_LDC, TH_LDCP, TH_TAB, TH_TABP, TH_ADDX, TH_ADDC, TH_MULX, TH_MULC, TH_NEG, TH_SQR,
+    TH_ABS, TH_ST, TH_ADDS, TH_MULS,
+    TH_CHEAP,
+    // TH_TABC = a tabulated function with a domain (sqrt, x^-1/2, log, asin, acos); TH_MOD = PUSH / SRCX modifiers of
+    // a function that has no table, followed by the function itself
+    TH_TABC = TH_CHEAP, TH_MOD,
+    TH_RECIP, TH_SQRT, TH_RSQRT, TH_POWI, TH_POWC, TH_EXP, TH_LOG, TH_SIN, TH_COS, TH_TAN, TH_ASIN, TH_ACOS,
+    TH_LDZ, TH_LDSPEC, TH_POWS,
+    TH_COUNT
+};
+static_assert(TH_CHEAP == 17 && TH_COUNT == 34, "the branch-target table in run_real lists the handlers by position");
+// program properties found while decoding
+constexpr uint32_t PF_NO_FAST = 1u;   // an instruction the IEEE fast path cannot express: every point takes run_cplx
+constexpr uint32_t PF_DEEP = 2u;      // uses spill slots >= CLOSYR_REG_SLOTS (kept in local memory by run_cplx)
+
+// handler of the elementary function CL_NEG + i
+__constant__ uint8_t closyr_th_of_function[CL_ABS - CL_NEG + 1] = {
+    TH_NEG, TH_RECIP, TH_SQR, TH_SQRT, TH_RSQRT, TH_POWI, TH_POWC, TH_EXP, TH_LOG, TH_SIN, TH_COS, TH_TAN, TH_ASIN, TH_ACOS, TH_ABS,
+};
+
+// the functions of the raw variable that closyr_set_points tabulates (bit = op - CL_RECIP):
+// RECIP SQRT RSQRT EXP LOG SIN COS TAN ASIN ACOS; SQR, POWI and POWC are not tabulated
+constexpr uint32_t VM_TAB_MASK = 0x1FCDu;
+
+// one ISA word -> one threaded-code entry; returns the PF_* bits the instruction implies
+__device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__restrict__ sconst, bool have_tab,
+                                                int64_t tab_stride, TInsn &t)
 {
-    Z slot[CLOSYR_MAX_SLOTS];
-    Z acc = zv(0.0, 0.0);
-#pragma unroll 1
-    for (int pc = 0;; pc++) {
-        const uint32_t w = scode[pc];
-        const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
-        const int b = (int)(w >> 16);
-        if (acc.re != acc.re) return acc;                   // Indeterminate absorbs every later instruction
-        // the frequent instructions first (slot forms, then Sin/Cos): the switch below compiles to a compare tree
-        if (op >= CL_ST0) {
-            if (op < CL_ADDS0) { slot[a] = acc; continue; }
-            const Z sl = slot[a];
-            if (sl.im == 0.0 && acc.im == 0.0) acc.re = op < CL_MULS0 ? sl.re + acc.re : sl.re * acc.re;
-            else acc = op < CL_MULS0 ? lean_add(sl, acc) : lean_mul(sl, acc);
-            continue;
-        }
-        const double *t = nullptr;
-        if ((a & (CL_M_PUSH | CL_M_SRCX)) && op < CL_ST && op != CL_LDSPEC) {   // ISA v1.1 modifiers
-            if (a & CL_M_PUSH) slot[CL_M_PUSH_SLOT(a)] = acc;
-            if (a & CL_M_SRCX) {
-                acc = zv(x, 0.0);
-                if (tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u))
-                    t = tab + (op - CL_RECIP) * tab_stride;
-            }
-        }
-        if (op == CL_SIN || op == CL_COS) {
-            if (acc.im == 0.0) acc.re = t ? *t : m_sincos(acc.re, (int)(op - CL_SIN));
-            else acc = op == CL_SIN ? zsin(acc) : zcos(acc);
-            continue;
-        }
-        switch (op) {
-        case CL_END: return acc;
-        case CL_LDX: acc = zv(x, 0.0); break;
-        case CL_LDC: acc = zv(sconst[b], 0.0); break;
-        case CL_LDZ: acc = zmk(sconst[b], sconst[b + 1]); break;
-        case CL_LDSPEC: acc = a == 0 ? zcinf() : zindet(); break;
-        case CL_ADDX: if (acc.im == 0.0) { acc.re += x; break; } CLOSYR_ZSET(lean_add(acc, zv(x, 0.0)))
-        case CL_ADDC: if (acc.im == 0.0) { acc.re += sconst[b]; break; } CLOSYR_ZSET(lean_add(acc, zv(sconst[b], 0.0)))
-        case CL_MULX: if (acc.im == 0.0) { acc.re *= x; break; } CLOSYR_ZSET(lean_mul(acc, zv(x, 0.0)))
-        case CL_MULC: if (acc.im == 0.0) { acc.re *= sconst[b]; break; } CLOSYR_ZSET(lean_mul(acc, zv(sconst[b], 0.0)))
-        case CL_NEG: CLOSYR_REAL1(true, -x_, zneg)
-        case CL_SQR: if (acc.im == 0.0) { acc.re = acc.re * acc.re; break; } CLOSYR_ZSET(lean_mul(acc, acc))
-        case CL_RECIP: CLOSYR_REAL1(x_ != 0.0, t ? *t : m_recip(x_), zrecip)
-        case CL_SQRT: CLOSYR_REAL1(x_ >= 0.0, t ? *t : m_sqrt(x_), zsqrt)
-        case CL_RSQRT: if (acc.im == 0.0 && acc.re > 0.0) { acc.re = t ? *t : m_recip(m_sqrt(acc.re)); break; } CLOSYR_ZSET(zrecip(zsqrt(acc)))
-        case CL_POWI: {
-            const int n = (int)(short)b;
-            if (acc.im == 0.0) {
-                const double r = powi_real(acc.re, n < 0 ? -n : n);
-                if (n > 0) acc.re = r;
-                else if (r != 0.0) acc.re = m_recip(r);
-                else acc = zcinf();
-                break;
-            }
-            CLOSYR_ZSET(zpowi(acc, n))
-        }
-        case CL_POWC: {
-            const double c = sconst[b];
-            if (acc.im == 0.0 && acc.re > 0.0 && !is_inf(acc.re) && !nonfinite(c) && c != 0.0) { acc.re = m_pow(acc.re, c); break; }
-            CLOSYR_ZSET(zpow(acc, zmk(c, 0.0)))
-        }
-        case CL_EXP: CLOSYR_REAL1(true, t ? *t : m_exp(x_), zexp)
-        case CL_LOG: CLOSYR_REAL1(x_ > 0.0, t ? *t : m_log(x_), zlog)
-        case CL_TAN: CLOSYR_REAL1(true, t ? *t : m_tan(x_), ztan)
-        case CL_ASIN: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : m_asin(x_), zasin)
-        case CL_ACOS: CLOSYR_REAL1(fabs(x_) <= 1.0, t ? *t : m_acos(x_), zacos)
-        case CL_ABS: CLOSYR_REAL1(true, fabs(x_), zabs)
-        default: {
-            // slot instructions: `a` is the slot for both the generic and the register forms
-            const uint32_t kind = op;                       // generic forms (the register forms were handled above)
-            if (kind == CL_ST) { slot[a] = acc; break; }
-            const Z sl = slot[a];
-            if (kind == CL_POWS) acc = zpow(sl, acc);
-            else if (sl.im == 0.0 && acc.im == 0.0) acc.re = kind == CL_ADDS ? sl.re + acc.re : sl.re * acc.re;
-            else acc = kind == CL_ADDS ? lean_add(sl, acc) : lean_mul(sl, acc);
-            break;
-        }
-        }
+    const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu, b = w >> 16;
+    const uint32_t mods = (a & 3u) | (((a >> 2) & 3u) << 10);          // SRCX, PUSH, push slot << 10
+    uint32_t pf = 0;
+    t.h = TH_END;
+    t.aux = b << 16;
+    t.c = 0.0;
+    if (op >= CL_ST && op < CL_NUM_OPCODES) {                          // slot forms, generic and register
+        t.h = op >= CL_ST0 ? (op < CL_ADDS0 ? TH_ST : (op < CL_MULS0 ? TH_ADDS : TH_MULS))
+                           : (op == CL_ST ? TH_ST : (op == CL_ADDS ? TH_ADDS : (op == CL_MULS ? TH_MULS : TH_POWS)));
+        const uint32_t k = a;                                          // the register forms repeat the slot in `a`
+        t.aux = k << 10;
+        if (k >= CLOSYR_REG_SLOTS) pf = PF_DEEP | PF_NO_FAST;
+        if (op == CL_POWS) pf |= PF_NO_FAST;
+        return pf;
     }
+    if (op >= CL_NEG && op <= CL_ABS) {
+        const uint32_t f = closyr_th_of_function[op - CL_NEG];
+        if (op == CL_POWC) {
+            t.c = sconst[b];
+            if (nonfinite(t.c) || t.c == 0.0) pf = PF_NO_FAST;
+        }
+        if ((a & CL_M_SRCX) && have_tab && op >= CL_RECIP && op <= CL_ACOS && ((VM_TAB_MASK >> (op - CL_RECIP)) & 1u)) {
+            // real on the whole line: sin cos exp tan 1/x; with a domain: sqrt x^-1/2 log asin acos
+            const bool total = op == CL_SIN || op == CL_COS || op == CL_EXP || op == CL_TAN || op == CL_RECIP;
+            t.h = total ? ((a & CL_M_PUSH) ? TH_TABP : TH_TAB) : TH_TABC;
+            t.aux = (mods & ~1u) | (f << 2);
+            t.c = __longlong_as_double((long long)(op - CL_RECIP) * tab_stride * 8);
+        } else if (a & (CL_M_SRCX | CL_M_PUSH)) {
+            t.h = TH_MOD;
+            t.aux = mods | (f << 2) | (b << 16);
+        } else t.h = f;
+        return pf;
+    }
+    switch (op) {
+    case CL_END: break;
+    case CL_LDX: t.h = (a & CL_M_PUSH) ? TH_LDXP : TH_LDX; t.aux = mods & ~1u; break;
+    case CL_LDC: t.h = (a & CL_M_PUSH) ? TH_LDCP : TH_LDC; t.aux = mods & ~1u; t.c = sconst[b]; break;
+    case CL_LDZ: t.h = TH_LDZ; pf = PF_NO_FAST; break;
+    case CL_LDSPEC: t.h = TH_LDSPEC; t.aux = a << 16; pf = PF_NO_FAST; break;
+    case CL_ADDX: t.h = TH_ADDX; break;
+    case CL_ADDC: t.h = TH_ADDC; t.c = sconst[b]; break;
+    case CL_MULX: t.h = TH_MULX; break;
+    case CL_MULC: t.h = TH_MULC; t.c = sconst[b]; break;
+    default:                                        // unknown opcode: stays symbolic in Symja, never a real number
+        t.h = TH_LDSPEC;
+        t.aux = 1u << 16;
+        pf = PF_NO_FAST;
+        break;
+    }
+    return pf;
 }
-#undef CLOSYR_ZSET
-#undef CLOSYR_REAL1
 
 // ------------------------------------------------------------------------------------------------
-// fast path: P points per lane, IEEE real arithmetic, register-resident accumulator and slots 0..3.
-//
-// Invariant kept per point (v = the IEEE value here, s = the value of the full algebra):
-//   v finite  <=>  s is a finite real and v == s;   v = +-Inf  =>  s is ComplexInfinity or a directed infinity
-//   (IEEE cannot tell which);   v NaN, no event  =>  s is Indeterminate (absorbing: the point is not real).
-// The returned mask has bit j set when point j must be re-evaluated with the complete algebra because the
-// invariant cannot be kept: an elementary function (anything but + * neg square) produced NaN from a non-NaN
-// input (it left its real domain: the algebra continues over the complex numbers) or was handed an infinity
-// (1/Inf = 0, E^-Inf = 0 ... are only right for some infinities); literals that are not real; general x^y.
+// shared-memory access by 32-bit shared-window address (through a generic pointer the compiler rebuilds the
+// window base at every access)
 // ------------------------------------------------------------------------------------------------
-#define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
-
-// spill slots are addressed with a 32-bit shared-window address computed once per evaluation: through a generic
-// pointer the compiler rebuilds the window base (S2UR CgaCtaId, UMOV, UIADD3, ULEA) at every access
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {
@@ -543,134 +523,636 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
-
-// All elementary-function instructions of the fast path, 4 points per call (the struct travels in registers):
-// four calls of the scalar routine per instruction, one copy of every routine in the kernel image.  Returns the values and the mask of points that need the complete algebra (see below).
-struct D4 { double v[4]; };
-struct R4 { D4 d; uint32_t ev; };
-
-__device__ __forceinline__ R4 k1_unary(uint32_t op, D4 in, double c)
+// x of this lane's points, loaded where an instruction needs it (L1-resident): with x in registers for the whole
+// program the 64-register budget spilled it to local memory.  volatile: the compiler would otherwise hoist the
+// loads of several handlers to the top of the dispatch loop.
+__device__ __forceinline__ void ldg_x(const double *p, double (&x)[4])
 {
-    R4 out;
-    double a[4] = { in.v[0], in.v[1], in.v[2], in.v[3] };
-#define CLOSYR_K4(expr) _Pragma("unroll") for (int j = 0; j < 4; j++) a[j] = (expr);
-    switch (op) {
-    case CL_EXP: CLOSYR_K4(m_exp(a[j])) break;
-    case CL_LOG: CLOSYR_K4(m_log(a[j])) break;
-    case CL_SIN: CLOSYR_K4(m_sincos(a[j], 0)) break;
-    case CL_COS: CLOSYR_K4(m_sincos(a[j], 1)) break;
-    case CL_RECIP: CLOSYR_K4(m_recip(a[j])) break;
-    case CL_SQRT: CLOSYR_K4(m_sqrt(a[j])) break;
-    case CL_TAN: CLOSYR_K4(m_tan(a[j])) break;
-    case CL_ASIN: CLOSYR_K4(m_asin(a[j])) break;
-    case CL_ACOS: CLOSYR_K4(m_acos(a[j])) break;
-    case CL_POWC: CLOSYR_K4(m_pow(a[j], c)) break;
-    default: CLOSYR_K4(u_real(op, a[j], c)) break;        // RSQRT POWI ABS
-    }
-#undef CLOSYR_K4
-    uint32_t ev = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const double i_ = in.v[j];
-        if (is_inf(i_) || (a[j] != a[j] && i_ == i_)) ev |= 1u << j;
-        out.d.v[j] = a[j];
-    }
-    out.ev = ev;
-    return out;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ double ldg_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// identity the optimiser cannot see through: keeps per-handler address arithmetic inside the handler
+__device__ __forceinline__ uint32_t opaque(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_insn(uint32_t addr)          // the threaded code is read-only while it runs
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 
-// Loop-carried state is only the accumulator (P doubles); x is loaded once per chunk.  The spill slots live
-// in shared memory ([slot][point][lane], conflict-free): with slots in registers the compiler copied the whole
-// 40-register state at every dispatch (36 % of all issued instructions were IMAD.MOV, ncu profile r01_c).
-template <int P>
-__device__ __forceinline__ uint32_t run_real(const uint32_t *__restrict__ scode, const double *__restrict__ sconst,
-                                             double *__restrict__ sslot, const double (&x)[P], double (&acc)[P],
-                                             const double *__restrict__ tab, int64_t tab_stride)
+// ------------------------------------------------------------------------------------------------
+// P-wide real elementary functions shared by run_real, the real mode of run_cplx and leaf_table_kernel, so a
+// value is bit-identical wherever it is computed
+// ------------------------------------------------------------------------------------------------
+#define CLOSYR_FORJ _Pragma("unroll") for (int j = 0; j < P; j++)
+
+template <int P> __device__ __forceinline__ void f_recip(double (&a)[P]) { CLOSYR_FORJ a[j] = 1.0 / a[j]; }
+template <int P> __device__ __forceinline__ void f_sqrt(double (&a)[P]) { CLOSYR_FORJ a[j] = sqrt(a[j]); }
+template <int P> __device__ __forceinline__ void f_rsqrt(double (&a)[P]) { CLOSYR_FORJ a[j] = 1.0 / sqrt(a[j]); }
+template <int P> __device__ __forceinline__ void f_tan(double (&a)[P]) { CLOSYR_FORJ a[j] = m_tan(a[j]); }
+template <int P> __device__ __forceinline__ void f_asin(double (&a)[P]) { CLOSYR_FORJ a[j] = m_asin(a[j]); }
+template <int P> __device__ __forceinline__ void f_acos(double (&a)[P]) { CLOSYR_FORJ a[j] = m_acos(a[j]); }
+template <int P> __device__ __forceinline__ void f_powc(double (&a)[P], double c) { CLOSYR_FORJ a[j] = m_pow(a[j], c); }
+// a^m by square-and-multiply, MSB first (the same chain the oracle walks); m >= 1; the loop is warp-uniform
+template <int P> __device__ __forceinline__ void f_powu(double (&a)[P], unsigned m)
 {
-    double ls[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];    // deep spill slots: local memory, rarely touched
+    double r[P];
+    CLOSYR_FORJ r[j] = a[j];
+#pragma unroll 1
+    for (int b = 30 - __clz((int)m); b >= 0; b--) {
+        CLOSYR_FORJ r[j] = r[j] * r[j];
+        if ((m >> b) & 1u) { CLOSYR_FORJ r[j] = r[j] * a[j]; }
+    }
+    CLOSYR_FORJ a[j] = r[j];
+}
+template <int P> __device__ __forceinline__ uint32_t mask_nonfinite(const double (&a)[P])
+{
+    uint32_t m = 0;
+    CLOSYR_FORJ if (nonfinite(a[j])) m |= 1u << j;
+    return m;
+}
+template <int P> __device__ __forceinline__ bool every_point_nan(const double (&a)[P])
+{
+    bool all = true;
+    CLOSYR_FORJ all = all && (abs_hi(a[j]) >= 0x7ff80000u);
+    return all;
+}
+
+// the tabulated functions of the raw variable, evaluated where no table exists (leaf_table_kernel fills the
+// tables through this very function)
+template <int P> __device__ __forceinline__ void f_tabulated(uint32_t op, double (&a)[P])
+{
+    switch (op) {
+    case CL_RECIP: f_recip<P>(a); break;
+    case CL_SQRT: f_sqrt<P>(a); break;
+    case CL_RSQRT: f_rsqrt<P>(a); break;
+    case CL_EXP: v_exp<P>(a); break;
+    case CL_LOG: v_log<P>(a); break;
+    case CL_SIN: v_sin<P>(a); break;
+    case CL_COS: v_cos<P>(a); break;
+    case CL_TAN: f_tan<P>(a); break;
+    case CL_ASIN: f_asin<P>(a); break;
+    default: f_acos<P>(a); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: P points per lane, IEEE real arithmetic, accumulator in registers, slots in shared memory
+// ([slot][point][lane] doubles, conflict-free; `slot_addr` is this lane's column).
+//
+// Invariant kept per point (v = the IEEE value here, s = the value of the full algebra):
+//   v finite, no report  <=>  s is a finite real and v == s;
+//   v = +-Inf            =>   s is ComplexInfinity, a directed infinity or Indeterminate (never a finite number;
+//                             the residual is max-resid either way, ops.clj:78-90)
+//   v NaN                =>   reported: NaN is absorbing through every instruction of this path, so a domain exit
+//                             (the algebra continues over the complex numbers) or an IEEE invalid operation
+//                             anywhere in the program shows in the result.
+// The returned mask has bit j set when point j must be re-evaluated with the complete algebra: its result is NaN,
+// or an instruction that maps an infinity to a finite number (1/Inf, E^-Inf, Inf^-k) was handed a non-finite
+// operand -- whether that is right depends on which infinity it was.
+// Programs with PF_NO_FAST never come here.
+// ------------------------------------------------------------------------------------------------
+// A function of its own (not inlined into the kernel): the dispatch loop gets a register allocation of its own.
+//
+// The cheap instructions (leaf loads, table loads, + and * with x / a literal / a slot, stores, neg, square, abs:
+// two thirds of all dispatches) are interpreted INSIDE one PTX block: LDS.128 of the threaded-code entry, brx.idx
+// through a branch-target table, the handler, back to the top -- 5 instructions of dispatch per handler.  Written
+// in C++, the same switch became a compare tree (NVVM has no jump tables) with register copies of the whole
+// accumulator at the loop head: 25 instructions per dispatch.  The block exits for the elementary functions, which
+// C++ handles below, and for END.
+template <int P> struct RealResult { double v[P]; uint32_t ev; };
+
+// The cheap handlers in PTX.  S = this copy's suffix, T = the other copy's: the loop is unrolled twice so that the
+// entry of the NEXT instruction is already being loaded (into the other copy's registers) while this one runs.
+// Operands: %0..%3 acc, %4 ip, %5..%8 = h aux c.lo c.hi of the instruction the block exits on, %9 this lane's slot
+// column, %10..%13 x, %14 table base of this lane's points.
+#define CLOSYR_PUSH_PTX(S)                   \
+    "and.b32 t_, aux" S "_, 0xc00;\n\t"      \
+    "add.u32 t_, t_, %9;\n\t"                \
+    "st.shared.f64 [t_], %0;\n\t"            \
+    "st.shared.f64 [t_+256], %1;\n\t"        \
+    "st.shared.f64 [t_+512], %2;\n\t"        \
+    "st.shared.f64 [t_+768], %3;\n\t"
+#define CLOSYR_OP4(OP, B0, B1, B2, B3)       \
+    OP " %0, %0, " B0 ";\n\t"                \
+    OP " %1, %1, " B1 ";\n\t"                \
+    OP " %2, %2, " B2 ";\n\t"                \
+    OP " %3, %3, " B3 ";\n\t"
+#define CLOSYR_CHEAP_HANDLERS(S, T)                                                            \
+    /* leaf loads: the P forms push acc first and fall through */                             \
+    "LDXP_" S ":\n\t" CLOSYR_PUSH_PTX(S)                                                       \
+    "LDX_" S ":\n\t"                                                                           \
+    "mov.f64 %0, %10;\n\t mov.f64 %1, %11;\n\t mov.f64 %2, %12;\n\t mov.f64 %3, %13;\n\t"       \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "LDCP_" S ":\n\t" CLOSYR_PUSH_PTX(S)                                                       \
+    "LDC_" S ":\n\t"                                                                           \
+    "mov.b64 %0, {lo" S "_, hi" S "_};\n\t mov.f64 %1, %0;\n\t mov.f64 %2, %0;\n\t mov.f64 %3, %0;\n\t" \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "TABP_" S ":\n\t" CLOSYR_PUSH_PTX(S)                                                       \
+    "TAB_" S ":\n\t" /* c = byte offset of the function's row */                               \
+    "mov.b64 ad_, {lo" S "_, hi" S "_};\n\t"                                                   \
+    "add.s64 ad_, ad_, %14;\n\t"                                                               \
+    "ld.global.nc.v2.f64 {%0, %1}, [ad_];\n\t"                                                 \
+    "ld.global.nc.v2.f64 {%2, %3}, [ad_+16];\n\t"                                              \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    /* arithmetic with a leaf operand (.rn: never contracted into an FMA) */                   \
+    "ADDX_" S ":\n\t" CLOSYR_OP4("add.rn.f64", "%10", "%11", "%12", "%13") "bra.uni NEXT_" T ";\n\t" \
+    "MULX_" S ":\n\t" CLOSYR_OP4("mul.rn.f64", "%10", "%11", "%12", "%13") "bra.uni NEXT_" T ";\n\t" \
+    "ADDC_" S ":\n\t"                                                                          \
+    "mov.b64 c_, {lo" S "_, hi" S "_};\n\t"                                                    \
+    CLOSYR_OP4("add.rn.f64", "c_", "c_", "c_", "c_") "bra.uni NEXT_" T ";\n\t"                 \
+    "MULC_" S ":\n\t"                                                                          \
+    "mov.b64 c_, {lo" S "_, hi" S "_};\n\t"                                                    \
+    CLOSYR_OP4("mul.rn.f64", "c_", "c_", "c_", "c_") "bra.uni NEXT_" T ";\n\t"                 \
+    "NEG_" S ":\n\t"                                                                           \
+    "neg.f64 %0, %0;\n\t neg.f64 %1, %1;\n\t neg.f64 %2, %2;\n\t neg.f64 %3, %3;\n\t"          \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "SQR_" S ":\n\t" CLOSYR_OP4("mul.rn.f64", "%0", "%1", "%2", "%3") "bra.uni NEXT_" T ";\n\t" \
+    "ABS_" S ":\n\t"                                                                           \
+    "abs.f64 %0, %0;\n\t abs.f64 %1, %1;\n\t abs.f64 %2, %2;\n\t abs.f64 %3, %3;\n\t"          \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    /* slots: aux = slot << 10 = its byte offset in this lane's column */                      \
+    "ST_" S ":\n\t"                                                                            \
+    "add.u32 t_, aux" S "_, %9;\n\t"                                                           \
+    "st.shared.f64 [t_], %0;\n\t st.shared.f64 [t_+256], %1;\n\t st.shared.f64 [t_+512], %2;\n\t st.shared.f64 [t_+768], %3;\n\t" \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "ADDS_" S ":\n\t"                                                                          \
+    "add.u32 t_, aux" S "_, %9;\n\t"                                                           \
+    "ld.shared.f64 s0_, [t_];\n\t ld.shared.f64 s1_, [t_+256];\n\t ld.shared.f64 s2_, [t_+512];\n\t ld.shared.f64 s3_, [t_+768];\n\t" \
+    CLOSYR_OP4("add.rn.f64", "s0_", "s1_", "s2_", "s3_") "bra.uni NEXT_" T ";\n\t"             \
+    "MULS_" S ":\n\t"                                                                          \
+    "add.u32 t_, aux" S "_, %9;\n\t"                                                           \
+    "ld.shared.f64 s0_, [t_];\n\t ld.shared.f64 s1_, [t_+256];\n\t ld.shared.f64 s2_, [t_+512];\n\t ld.shared.f64 s3_, [t_+768];\n\t" \
+    CLOSYR_OP4("mul.rn.f64", "s0_", "s1_", "s2_", "s3_") "bra.uni NEXT_" T ";\n\t"             \
+    /* dispatch of this copy: start loading the following entry into the other copy's registers, then jump */ \
+    "NEXT_" S ":\n\t"                                                                          \
+    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%4+16];\n\t"                  \
+    "add.u32 %4, %4, 16;\n\t"                                                                  \
+    "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", ADDX_" S ", ADDC_" S \
+    ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S                             \
+    ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S   \
+    ", X_" S ", X_" S ", X_" S ", X_" S ";\n\t"                                                \
+    "brx.idx.uni h" S "_, tbl" S "_;\n\t"                                                      \
+    /* not a cheap instruction: hand it to the C++ part (ip already points at the following entry) */ \
+    "X_" S ":\n\t"                                                                             \
+    "mov.b32 %5, h" S "_;\n\t mov.b32 %6, aux" S "_;\n\t mov.b32 %7, lo" S "_;\n\t mov.b32 %8, hi" S "_;\n\t" \
+    "bra.uni OUT_;\n\t"
+
+template <int P>
+__device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const uint32_t slot_addr,
+                                               const double *__restrict__ xp, const double *__restrict__ tab)
+{
+    constexpr uint32_t ALL = (1u << P) - 1u;
+    static_assert(P == 4, "slot stride and x loads are written for 4 points per lane");
+    RealResult<P> res;
+    double (&acc)[P] = res.v;
     uint32_t ev = 0;
-    int pc = 0;
-    uint32_t w = scode[0];
-    const uint32_t slot_base = (uint32_t)__cvta_generic_to_shared(sslot);
+    uint32_t ip = tcode_addr;
+    double x[P];
+    ldg_x(xp, x);
     CLOSYR_FORJ acc[j] = 0.0;
+#define CLOSYR_PUSH_IF()                                                       \
+    if (aux & 2u) {                                                            \
+        const uint32_t sl_ = slot_addr + (aux & 0xc00u);                       \
+        CLOSYR_FORJ sts_f64(sl_ + j * 256, acc[j]);                            \
+    }
 #pragma unroll 1
     for (;;) {
-        const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu;
-        const int b = (int)(w >> 16);
-        w = scode[++pc];                                     // prefetch (the buffer has one word of slack)
-        if (op < CL_ST && (a & (CL_M_PUSH | CL_M_SRCX)) && op != CL_LDSPEC) {
-            // ISA v1.1 modifiers of the leaf loads and the elementary functions: push acc, read x
-            if (a & CL_M_PUSH) {
-                const uint32_t sl = slot_base + CL_M_PUSH_SLOT(a) * (P * 32 * 8);
-                CLOSYR_FORJ sts_f64(sl + j * 256, acc[j]);
-            }
-            if (a & CL_M_SRCX) { CLOSYR_FORJ acc[j] = x[j]; }
+        uint32_t h, aux, clo, chi;
+        asm volatile(
+            "{\n\t"
+            ".reg .b32 t_, hA_, auxA_, loA_, hiA_, hB_, auxB_, loB_, hiB_;\n\t"
+            ".reg .b64 ad_;\n\t"
+            ".reg .f64 c_, s0_, s1_, s2_, s3_;\n\t"
+            "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%4];\n\t"
+            "bra.uni NEXT_A;\n\t"
+            CLOSYR_CHEAP_HANDLERS("A", "B")
+            CLOSYR_CHEAP_HANDLERS("B", "A")
+            "OUT_:\n\t"
+            "}\n"
+            : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+r"(ip), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
+            : "r"(slot_addr), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "l"(tab)
+            : "memory");
+        const double c = __hiloint2double((int)chi, (int)clo);
+    redo:
+        switch (h) {
+        case TH_END: {
+            CLOSYR_FORJ if (acc[j] != acc[j]) ev |= 1u << j;
+            res.ev = ev;
+            return res;
         }
-        if (op >= CL_ST0) {
-            // register-file-free slot forms: CL_ST0+a, CL_ADDS0+a, CL_MULS0+a with a in 0..3
-            const uint32_t sl = slot_base + a * (P * 32 * 8);
-            if (op < CL_ADDS0) { CLOSYR_FORJ sts_f64(sl + j * 256, acc[j]); }
-            else if (op < CL_MULS0) { CLOSYR_FORJ acc[j] = lds_f64(sl + j * 256) + acc[j]; }
-            else { CLOSYR_FORJ acc[j] = lds_f64(sl + j * 256) * acc[j]; }
-            continue;
+        case TH_TABC: {
+            // f(x) of the raw variable, tabulated per point by leaf_table_kernel with the same routines, for a function
+            // with a domain.  Points are sorted by x, so a domain exit usually takes whole chunks: once every point of
+            // the warp is lost the rest of the fast pass is wasted work (the complete algebra starts over anyway)
+            CLOSYR_PUSH_IF()
+            ldg_x(reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c)), acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            break;
         }
-        switch (op) {
-        case CL_END: return ev;
-        case CL_LDX: CLOSYR_FORJ acc[j] = x[j]; break;
-        case CL_LDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = c; break; }
-        case CL_ADDX: CLOSYR_FORJ acc[j] = acc[j] + x[j]; break;
-        case CL_ADDC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] + c; break; }
-        case CL_MULX: CLOSYR_FORJ acc[j] = acc[j] * x[j]; break;
-        case CL_MULC: { const double c = sconst[b]; CLOSYR_FORJ acc[j] = acc[j] * c; break; }
-        case CL_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;
-        case CL_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
-        case CL_ST:
-            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ ls[a - CLOSYR_REG_SLOTS][j] = acc[j]; }
-            else ev = (1u << P) - 1u;
+        case TH_MOD:                                         // PUSH / SRCX modifiers of a function that has no table
+            CLOSYR_PUSH_IF()
+            if (aux & 1u) { CLOSYR_FORJ acc[j] = x[j]; }
+            h = (aux >> 2) & 0xffu;
+            goto redo;
+        case TH_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;      // reached through TH_MOD only
+        case TH_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
+        case TH_ABS: CLOSYR_FORJ acc[j] = fabs(acc[j]); break;
+        case TH_RECIP: ev |= mask_nonfinite<P>(acc); f_recip<P>(acc); break;
+        case TH_SQRT:
+            f_sqrt<P>(acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
             break;
-        case CL_ADDS:
-            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ acc[j] = ls[a - CLOSYR_REG_SLOTS][j] + acc[j]; }
-            else ev = (1u << P) - 1u;
+        case TH_RSQRT:
+            ev |= mask_nonfinite<P>(acc);
+            f_rsqrt<P>(acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
             break;
-        case CL_MULS:
-            if (a >= CLOSYR_REG_SLOTS) { CLOSYR_FORJ acc[j] = ls[a - CLOSYR_REG_SLOTS][j] * acc[j]; }
-            else ev = (1u << P) - 1u;
+        case TH_POWI: {
+            const int n = (int)(short)(aux >> 16);
+            if (n < 0) {
+                ev |= mask_nonfinite<P>(acc);
+                f_powu<P>(acc, (unsigned)-n);
+                f_recip<P>(acc);
+            } else f_powu<P>(acc, (unsigned)n);
             break;
-        case CL_LDZ:
-        case CL_LDSPEC:
-        case CL_POWS: return (1u << P) - 1u;                 // program-uniform: every point needs the complete algebra
-        default: {
-            // every other instruction is a real elementary function of the accumulator
-            double c = (double)(short)b;
-            if (op == CL_POWC) {
-                c = sconst[b];
-                if (nonfinite(c) || c == 0.0) { ev = (1u << P) - 1u; break; }
+        }
+        case TH_POWC:
+            ev |= mask_nonfinite<P>(acc);
+            f_powc<P>(acc, c);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            break;
+        case TH_EXP: ev |= mask_nonfinite<P>(acc); v_exp<P>(acc); break;
+        case TH_LOG:
+            v_log<P>(acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            break;
+        case TH_SIN: v_sin<P>(acc); break;
+        case TH_COS: v_cos<P>(acc); break;
+        case TH_TAN: f_tan<P>(acc); break;
+        case TH_ASIN:
+            f_asin<P>(acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            break;
+        case TH_ACOS:
+            f_acos<P>(acc);
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            break;
+        default: { res.ev = ALL; return res; }                 // LDZ LDSPEC POWS: PF_NO_FAST programs do not come here
+        }
+    }
+#undef CLOSYR_PUSH_IF
+}
+#undef CLOSYR_CHEAP_HANDLERS
+#undef CLOSYR_OP4
+#undef CLOSYR_PUSH_PTX
+
+// ------------------------------------------------------------------------------------------------
+// complete algebra, P points per lane.  (re, im) per point with the encoding of Z: Indeterminate = NaN real part,
+// ComplexInfinity = (Inf, Inf), directed infinities = (+-Inf, 0).
+//
+// Real mode (cmo == 0): every value of the accumulator is a real number, a directed infinity or Indeterminate; the
+// imaginary parts are not maintained.  IEEE arithmetic IS the algebra there for + and * (oracle v_add / v_mul on two
+// T_REAL values), and every elementary function checks the condition under which its real routine is the algebra's
+// value; the first point that fails it takes the whole warp to complex mode (cmo == TH_COUNT: the handler index is
+// offset into the second half of the jump table) and the instruction is dispatched again there.  Leaf loads return
+// to real mode.  `sm` has bit k set when slot k holds values with imaginary parts.
+//
+// Complex mode: + and * are the finite formulas of lean_add / lean_mul for all points at once; a point whose result
+// is not finite (an operand was an infinity / Indeterminate, or the arithmetic overflowed) is redone by zadd / zmul.
+// Elementary functions go point by point through the z* functions (they hold the case analysis of the algebra).
+//
+// Slots: [slot][re | im][point][lane] doubles in shared memory for slots 0..3 (the same bytes run_real uses: its
+// values are dead by now), local memory beyond.
+// ------------------------------------------------------------------------------------------------
+template <int P> struct CAcc { double re[P], im[P]; };
+
+// the chop of zmk on a finite result
+__device__ __forceinline__ void c_chop(double &re, double &im)
+{
+    if (im != 0.0 && fabs(im) <= CLOSYR_CHOP_REL * fabs(re)) im = 0.0;
+    else if (re != 0.0 && fabs(re) <= CLOSYR_CHOP_REL * fabs(im)) re = 0.0;
+}
+// acc = s + acc (s = the other operand; + commutes bit for bit, zadd is symmetric)
+template <int P>
+__device__ __forceinline__ void c_add(CAcc<P> &a, const double (&sre)[P], const double (&sim)[P])
+{
+    double rr[P], ri[P];
+    uint32_t bad = 0;
+    CLOSYR_FORJ {
+        rr[j] = sre[j] + a.re[j];
+        ri[j] = sim[j] + a.im[j];
+        if (nonfinite(rr[j]) || nonfinite(ri[j])) bad |= 1u << j;
+        c_chop(rr[j], ri[j]);
+    }
+    if (bad) {                                   // an operand is an infinity / Indeterminate, or the sum overflowed
+        CLOSYR_FORJ if ((bad >> j) & 1u) {
+            const Z r = zadd(zv(sre[j], sim[j]), zv(a.re[j], a.im[j]));
+            rr[j] = r.re;
+            ri[j] = r.im;
+        }
+    }
+    CLOSYR_FORJ { a.re[j] = rr[j]; a.im[j] = ri[j]; }
+}
+// acc = s * acc with lean_mul's case split on the operands' imaginary parts (s first, as the scalar code has it)
+template <int P>
+__device__ __forceinline__ void c_mul(CAcc<P> &a, const double (&sre)[P], const double (&sim)[P])
+{
+    double rr[P], ri[P];
+    uint32_t bad = 0;
+    CLOSYR_FORJ {
+        const double p1 = sre[j] * a.re[j], p2 = sim[j] * a.im[j], p3 = sre[j] * a.im[j], p4 = sim[j] * a.re[j];
+        const bool s_real = sim[j] == 0.0, a_real = a.im[j] == 0.0;
+        rr[j] = (s_real || a_real) ? p1 : p1 - p2;
+        ri[j] = s_real ? p3 : (a_real ? p4 : p3 + p4);
+        if (nonfinite(rr[j]) || nonfinite(ri[j])) bad |= 1u << j;
+        c_chop(rr[j], ri[j]);
+    }
+    if (bad) {
+        CLOSYR_FORJ if ((bad >> j) & 1u) {
+            const Z r = zmul(zv(sre[j], sim[j]), zv(a.re[j], a.im[j]));
+            rr[j] = r.re;
+            ri[j] = r.im;
+        }
+    }
+    CLOSYR_FORJ { a.re[j] = rr[j]; a.im[j] = ri[j]; }
+}
+
+#define CLOSYR_ZCALL(f)                                            \
+    CLOSYR_FORJ {                                                  \
+        const Z r_ = f(zv(a.re[j], a.im[j]));                      \
+        a.re[j] = r_.re;                                           \
+        a.im[j] = r_.im;                                           \
+    }
+
+// real-mode integer power of the scalar interpreter: |n| by the multiplication chain, then 1/r, ComplexInfinity at 0
+__device__ __noinline__ Z zpowi_any(Z a, int n)
+{
+    if (a.im == 0.0) {
+        const double r = powi_real(a.re, n < 0 ? -n : n);
+        if (n > 0) return zv(r, 0.0);
+        if (r != 0.0) return zv(1.0 / r, 0.0);
+        return zcinf();
+    }
+    return zpowi(a, n);
+}
+__device__ __noinline__ Z zrsqrt(Z a) { return zrecip(zsqrt(a)); }
+
+// Evaluates the program on this lane's P points.  out[j] = the value when it is a real number (possibly +-Inf);
+// nonreal = the mask of points whose value is NOT a real number (eval.clj:70-80 turns those into +Inf).
+// `tab` = base of the f(x_i) tables (or nullptr), idx[j] = the point's index.  Must be called by whole warps.
+template <int P> struct CplxArgs { int64_t idx[P]; };
+template <int P> struct CplxResult { double out[P]; uint32_t nonreal; };
+
+template <int P>
+__device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const uint32_t slot_addr,
+                                               const double *__restrict__ sconst, const double *__restrict__ xs,
+                                               const CplxArgs<P> args, const double *__restrict__ tab)
+{
+    const int64_t (&idx)[P] = args.idx;
+    constexpr unsigned FULLW = 0xffffffffu;
+    constexpr uint32_t SLOT_SHIFT = 10;                     // 1 KiB per slot, as run_real<4>: [re|im][P points][32 lanes]
+    constexpr uint32_t IM_OFF = 512;
+    static_assert(P == 2, "slot layout is written for 2 points per lane");
+    CAcc<P> a;
+    Z deep[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];         // local memory, touched by PF_DEEP programs only
+    uint32_t cmo = 0;                                        // 0 real mode, TH_COUNT complex mode
+    uint32_t sm = 0;                                         // slots holding imaginary parts
+    uint32_t ip = tcode_addr;
+    uint4 nx = lds_insn(ip);
+    CLOSYR_FORJ { a.re[j] = 0.0; a.im[j] = 0.0; }
+#define CLOSYR_TO_COMPLEX() { CLOSYR_FORJ a.im[j] = 0.0; cmo = TH_COUNT; }
+#define CLOSYR_STORE(k_)                                                                    \
+    {                                                                                       \
+        const uint32_t k = (k_);                                                            \
+        if (k < CLOSYR_REG_SLOTS) {                                                         \
+            const uint32_t sl_ = slot_addr + (k << SLOT_SHIFT);                             \
+            CLOSYR_FORJ sts_f64(sl_ + j * 256, a.re[j]);                                    \
+            if (cmo) { CLOSYR_FORJ sts_f64(sl_ + IM_OFF + j * 256, a.im[j]); sm |= 1u << k; } \
+            else sm &= ~(1u << k);                                                          \
+        } else {                                                                            \
+            CLOSYR_FORJ deep[k - CLOSYR_REG_SLOTS][j] = zv(a.re[j], cmo ? a.im[j] : 0.0);   \
+        }                                                                                   \
+    }
+#define CLOSYR_PUSH_IF() if (aux & 2u) CLOSYR_STORE((opaque(aux) >> 10) & 3u)
+#define CLOSYR_LOADX(dst) CLOSYR_FORJ dst[j] = ldg_f64(xs + idx[j]);
+    // loads slot k into (sre, sim); `scx` = the slot may hold imaginary parts
+#define CLOSYR_LOAD(k_)                                                                     \
+    double sre[P], sim[P];                                                                  \
+    bool scx;                                                                               \
+    {                                                                                       \
+        const uint32_t k = (k_);                                                            \
+        if (k < CLOSYR_REG_SLOTS) {                                                         \
+            const uint32_t sl_ = slot_addr + (k << SLOT_SHIFT);                             \
+            scx = (sm >> k) & 1u;                                                           \
+            CLOSYR_FORJ sre[j] = lds_f64(sl_ + j * 256);                                    \
+            if (scx) { CLOSYR_FORJ sim[j] = lds_f64(sl_ + IM_OFF + j * 256); }              \
+            else { CLOSYR_FORJ sim[j] = 0.0; }                                              \
+        } else {                                                                            \
+            scx = true;                                                                     \
+            CLOSYR_FORJ { sre[j] = deep[k - CLOSYR_REG_SLOTS][j].re; sim[j] = deep[k - CLOSYR_REG_SLOTS][j].im; } \
+        }                                                                                   \
+    }
+    // real-mode elementary function: `cond` (per point, on x_ = a.re[j]) says the real routine is the algebra's value
+#define CLOSYR_REALF(cond, body)                                                            \
+    {                                                                                       \
+        bool ok_ = true;                                                                    \
+        CLOSYR_FORJ { const double x_ = a.re[j]; ok_ = ok_ && (cond); }                     \
+        if (__all_sync(FULLW, ok_)) { body; break; }                                        \
+        CLOSYR_TO_COMPLEX()                                                                 \
+        h += TH_COUNT;                                                                      \
+        goto redo;                                                                          \
+    }
+#pragma unroll 1
+    for (;;) {
+        uint32_t h = nx.x + cmo;
+        const uint32_t aux = nx.y;
+        const double c = __hiloint2double((int)nx.w, (int)nx.z);
+        ip += 16;
+        nx = lds_insn(ip);
+    redo:
+        switch (h) {
+        case TH_END:
+        case TH_END + TH_COUNT: {
+            CplxResult<P> res;
+            res.nonreal = 0;
+            CLOSYR_FORJ {
+                const bool real = a.re[j] == a.re[j] && (cmo == 0 || a.im[j] == 0.0);
+                if (!real) res.nonreal |= 1u << j;
+                res.out[j] = a.re[j];
             }
-            static_assert(P == 4, "k1_unary is written for 4 points per lane");
-            if ((a & CL_M_SRCX) && tab != nullptr && op >= CL_RECIP && op <= CL_ACOS && ((0x1FCDu >> (op - CL_RECIP)) & 1u)) {
-                // f(x) of the raw variable: tabulated per point by leaf_table_kernel with the same routines
-                // (`tab` points at this lane's first point); the report rule is k1_unary's
-                const double2 t0 = *reinterpret_cast<const double2 *>(tab + (op - CL_RECIP) * tab_stride);
-                const double2 t1 = *reinterpret_cast<const double2 *>(tab + (op - CL_RECIP) * tab_stride + 2);
-                acc[0] = t0.x; acc[1] = t0.y; acc[2] = t1.x; acc[3] = t1.y;
-                uint32_t e4 = 0;
-                CLOSYR_FORJ if (is_inf(x[j]) || (acc[j] != acc[j] && x[j] == x[j])) e4 |= 1u << j;
-                ev |= e4;
-            } else {
-                D4 in;
-                CLOSYR_FORJ in.v[j] = acc[j];
-                const R4 r = k1_unary(op, in, c);
-                CLOSYR_FORJ acc[j] = r.d.v[j];
-                ev |= r.ev;
+            return res;
+        }
+        // ---- leaf loads: back to real mode
+        case TH_LDX:
+        case TH_LDXP:
+        case TH_LDX + TH_COUNT:
+        case TH_LDXP + TH_COUNT: CLOSYR_PUSH_IF() CLOSYR_LOADX(a.re) cmo = 0; break;
+        case TH_LDC:
+        case TH_LDCP:
+        case TH_LDC + TH_COUNT:
+        case TH_LDCP + TH_COUNT: CLOSYR_PUSH_IF() CLOSYR_FORJ a.re[j] = c; cmo = 0; break;
+        case TH_TAB:
+        case TH_TABP:
+        case TH_TABC:
+        case TH_TAB + TH_COUNT:
+        case TH_TABP + TH_COUNT:
+        case TH_TABC + TH_COUNT: {
+            CLOSYR_PUSH_IF()
+            const double *row = reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c));
+            double t[P];
+            bool fin = true;
+            CLOSYR_FORJ { t[j] = row[idx[j]]; fin = fin && !nonfinite(t[j]); }
+            cmo = 0;
+            if (__all_sync(FULLW, fin)) { CLOSYR_FORJ a.re[j] = t[j]; break; }
+            // some point is off the function's real domain (or at a pole): the function itself, complex mode
+            CLOSYR_LOADX(a.re)
+            CLOSYR_TO_COMPLEX()
+            h = ((aux >> 2) & 0xffu) + TH_COUNT;
+            goto redo;
+        }
+        case TH_MOD:
+        case TH_MOD + TH_COUNT:
+            CLOSYR_PUSH_IF()
+            if (aux & 1u) { CLOSYR_LOADX(a.re) cmo = 0; }
+            h = ((aux >> 2) & 0xffu) + cmo;
+            goto redo;
+        case TH_LDZ:
+        case TH_LDZ + TH_COUNT: {
+            const Z z = zmk(sconst[aux >> 16], sconst[(aux >> 16) + 1]);
+            CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
+            cmo = TH_COUNT;
+            break;
+        }
+        case TH_LDSPEC:
+        case TH_LDSPEC + TH_COUNT: {
+            const Z z = (aux >> 16) == 0 ? zcinf() : zindet();
+            CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
+            cmo = TH_COUNT;
+            break;
+        }
+        // ---- real mode: IEEE arithmetic is the algebra
+        case TH_ADDX: { double x[P]; CLOSYR_LOADX(x) CLOSYR_FORJ a.re[j] = a.re[j] + x[j]; break; }
+        case TH_ADDC: CLOSYR_FORJ a.re[j] = a.re[j] + c; break;
+        case TH_MULX: { double x[P]; CLOSYR_LOADX(x) CLOSYR_FORJ a.re[j] = a.re[j] * x[j]; break; }
+        case TH_MULC: CLOSYR_FORJ a.re[j] = a.re[j] * c; break;
+        case TH_NEG: CLOSYR_FORJ a.re[j] = -a.re[j]; break;
+        case TH_SQR: CLOSYR_FORJ a.re[j] = a.re[j] * a.re[j]; break;
+        case TH_ABS: CLOSYR_FORJ a.re[j] = fabs(a.re[j]); break;
+        case TH_ST:
+        case TH_ST + TH_COUNT: CLOSYR_STORE(opaque(aux) >> 10) break;
+        case TH_ADDS:
+        case TH_MULS: {
+            const uint32_t k = opaque(aux) >> 10;
+            const bool scx = k >= CLOSYR_REG_SLOTS || ((sm >> k) & 1u);
+            if (scx) {
+                CLOSYR_TO_COMPLEX()
+                h += TH_COUNT;
+                goto redo;
             }
-            // points are sorted by x, so a domain exit usually takes whole chunks: once every point of the warp is
-            // reported the rest of the fast pass is wasted work (the complete algebra starts over anyway)
-            if (__all_sync(0xffffffffu, ev == (1u << P) - 1u)) return ev;
+            const uint32_t sl = slot_addr + (k << SLOT_SHIFT);
+            if (h == TH_ADDS) { CLOSYR_FORJ a.re[j] = lds_f64(sl + j * 256) + a.re[j]; }
+            else { CLOSYR_FORJ a.re[j] = lds_f64(sl + j * 256) * a.re[j]; }
+            break;
+        }
+        case TH_RECIP: CLOSYR_REALF(x_ != 0.0, f_recip<P>(a.re))
+        case TH_SQRT: CLOSYR_REALF(!(x_ < 0.0), f_sqrt<P>(a.re))
+        case TH_RSQRT: CLOSYR_REALF(!(x_ <= 0.0), f_rsqrt<P>(a.re))
+        case TH_POWI: {
+            const int n = (int)(short)(aux >> 16);
+            double r[P];
+            CLOSYR_FORJ r[j] = a.re[j];
+            f_powu<P>(r, (unsigned)(n < 0 ? -n : n));
+            if (n > 0) { CLOSYR_FORJ a.re[j] = r[j]; break; }
+            bool ok = true;
+            CLOSYR_FORJ ok = ok && (r[j] != 0.0);
+            if (__all_sync(FULLW, ok)) { CLOSYR_FORJ a.re[j] = 1.0 / r[j]; break; }
+            CLOSYR_TO_COMPLEX()
+            h += TH_COUNT;
+            goto redo;
+        }
+        case TH_POWC: CLOSYR_REALF(x_ > 0.0 && !is_inf(x_) && !nonfinite(c) && c != 0.0, f_powc<P>(a.re, c))
+        case TH_EXP: v_exp<P>(a.re); break;
+        case TH_LOG: CLOSYR_REALF(!(x_ <= 0.0), v_log<P>(a.re))
+        case TH_SIN: v_sin<P>(a.re); break;
+        case TH_COS: v_cos<P>(a.re); break;
+        case TH_TAN: f_tan<P>(a.re); break;
+        case TH_ASIN: CLOSYR_REALF(!(fabs(x_) > 1.0), f_asin<P>(a.re))
+        case TH_ACOS: CLOSYR_REALF(!(fabs(x_) > 1.0), f_acos<P>(a.re))
+        case TH_POWS: CLOSYR_TO_COMPLEX() h += TH_COUNT; goto redo;
+        // ---- complex mode
+        case TH_ADDX + TH_COUNT: { double x[P], zr[P]; CLOSYR_LOADX(x) CLOSYR_FORJ zr[j] = 0.0; c_add<P>(a, x, zr); break; }
+        case TH_MULX + TH_COUNT: { double x[P], zr[P]; CLOSYR_LOADX(x) CLOSYR_FORJ zr[j] = 0.0; c_mul<P>(a, x, zr); break; }
+        case TH_ADDC + TH_COUNT: { double cr[P], zr[P]; CLOSYR_FORJ { cr[j] = c; zr[j] = 0.0; } c_add<P>(a, cr, zr); break; }
+        case TH_MULC + TH_COUNT: { double cr[P], zr[P]; CLOSYR_FORJ { cr[j] = c; zr[j] = 0.0; } c_mul<P>(a, cr, zr); break; }
+        case TH_NEG + TH_COUNT: CLOSYR_ZCALL(zneg) break;
+        case TH_SQR + TH_COUNT: { double sr[P], si[P]; CLOSYR_FORJ { sr[j] = a.re[j]; si[j] = a.im[j]; } c_mul<P>(a, sr, si); break; }
+        case TH_ABS + TH_COUNT: CLOSYR_ZCALL(zabs) break;
+        case TH_ADDS + TH_COUNT: { CLOSYR_LOAD(opaque(aux) >> 10) (void)scx; c_add<P>(a, sre, sim); break; }
+        case TH_MULS + TH_COUNT: { CLOSYR_LOAD(opaque(aux) >> 10) (void)scx; c_mul<P>(a, sre, sim); break; }
+        case TH_POWS + TH_COUNT: {
+            CLOSYR_LOAD(opaque(aux) >> 10)
+            (void)scx;
+            CLOSYR_FORJ {
+                const Z r = zpow(zv(sre[j], sim[j]), zv(a.re[j], a.im[j]));
+                a.re[j] = r.re;
+                a.im[j] = r.im;
+            }
+            break;
+        }
+        case TH_RECIP + TH_COUNT: CLOSYR_ZCALL(zrecip) break;
+        case TH_SQRT + TH_COUNT: CLOSYR_ZCALL(zsqrt) break;
+        case TH_RSQRT + TH_COUNT: CLOSYR_ZCALL(zrsqrt) break;
+        case TH_POWI + TH_COUNT: {
+            const int n = (int)(short)(aux >> 16);
+            CLOSYR_FORJ {
+                const Z r = zpowi_any(zv(a.re[j], a.im[j]), n);
+                a.re[j] = r.re;
+                a.im[j] = r.im;
+            }
+            break;
+        }
+        case TH_POWC + TH_COUNT: {
+            const Z w = zmk(c, 0.0);
+            CLOSYR_FORJ {
+                const Z r = zpow(zv(a.re[j], a.im[j]), w);
+                a.re[j] = r.re;
+                a.im[j] = r.im;
+            }
+            break;
+        }
+        case TH_EXP + TH_COUNT: CLOSYR_ZCALL(zexp) break;
+        case TH_LOG + TH_COUNT: CLOSYR_ZCALL(zlog) break;
+        case TH_SIN + TH_COUNT: CLOSYR_ZCALL(zsin) break;
+        case TH_COS + TH_COUNT: CLOSYR_ZCALL(zcos) break;
+        case TH_TAN + TH_COUNT: CLOSYR_ZCALL(ztan) break;
+        case TH_ASIN + TH_COUNT: CLOSYR_ZCALL(zasin) break;
+        case TH_ACOS + TH_COUNT: CLOSYR_ZCALL(zacos) break;
+        default: {                                           // cannot happen: decode_insn emits the handlers above only
+            CLOSYR_FORJ { a.re[j] = __longlong_as_double(0x7ff8000000000000ll); a.im[j] = 0.0; }
+            cmo = TH_COUNT;
             break;
         }
         }
     }
+#undef CLOSYR_REALF
+#undef CLOSYR_LOADX
+#undef CLOSYR_LOAD
+#undef CLOSYR_PUSH_IF
+#undef CLOSYR_STORE
+#undef CLOSYR_TO_COMPLEX
 }
+#undef CLOSYR_ZCALL
 
 }  // namespace dev
 }  // namespace closyr

@@ -199,6 +199,10 @@ int closyr_l2_flush(closyr_ctx *ctx);
 int closyr_fp64_peak_probe(closyr_ctx *ctx, double *dfma_per_second); /* register-resident DFMA chain */
 int64_t closyr_kernel_launch_count(const closyr_ctx *ctx);
 
+/* self test (no GPU needed): the builder's buffer falls back to pageable memory when page-locked memory runs out
+ * and releases every block with the allocator it came from; 0 = ok */
+int closyr_selftest_pinned_fallback(void);
+
 /* pinned host memory for population buffers written directly by the caller (FFM MemorySegment) */
 void *closyr_host_alloc(size_t bytes);
 void closyr_host_free(void *p);

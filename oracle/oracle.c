@@ -50,8 +50,12 @@
  * large x), tests evaluate the oracle again with every transcendental result nudged by one ulp up / down and
  * only hold the 1e-9 bar where the oracle agrees with itself.  0 = off (default). */
 static int g_jitter = 0;                      /* 0 off; otherwise the seed of a random +-1 ulp pattern */
+static int g_jitter_ulps = 1;                 /* amplitude: each result moves by 1 .. g_jitter_ulps ulp, either way */
 static _Thread_local uint64_t t_jcnt = 0;     /* position in the pattern; reset per expression */
 void oracle_set_jitter(int seed) { g_jitter = seed; }
+/* CUDA's own libm documents up to 2 ulp for sin cos tan asin acos pow (1 ulp for exp log); the explanation probes
+ * (oracle.py *_discrepancy_explained) use that envelope, the stability masks keep +-1 ulp */
+void oracle_set_jitter_ulps(int ulps) { g_jitter_ulps = ulps < 1 ? 1 : ulps; }
 static double J(double r)
 {
     if (g_jitter == 0 || !isfinite(r)) return r;
@@ -59,7 +63,10 @@ static double J(double r)
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    return nextafter(r, (z & 1) ? INFINITY : -INFINITY);
+    const double dir = (z & 1) ? INFINITY : -INFINITY;
+    int steps = 1 + (int)((z >> 1) % (uint64_t)g_jitter_ulps);
+    while (steps-- > 0) r = nextafter(r, dir);
+    return r;
 }
 #define exp(x) J(exp(x))
 #define log(x) J(log(x))

@@ -55,6 +55,8 @@ def lib():
         L.oracle_tree_partial.restype = None
         L.oracle_set_jitter.argtypes = [C.c_int]
         L.oracle_set_jitter.restype = None
+        L.oracle_set_jitter_ulps.argtypes = [C.c_int]
+        L.oracle_set_jitter_ulps.restype = None
         _lib = L
     return _lib
 
@@ -138,6 +140,11 @@ def max_threads():
     return lib().oracle_max_threads()
 
 
+# Envelope of the explanation probes: the math library under test may be up to 2 ulp off (CUDA's documented bound for
+# sin cos tan asin acos pow; this repo's own routines state <= 2 ulp), the oracle's glibc about 0.5 ulp.
+EXPLAIN_ULPS = 2
+
+
 def score_batch_conditioned(exprs, xs, ys, max_leafs=40, sum_mode=SUM_LEFT_FOLD, tol=1e-10, probes=8):
     """Scores plus a mask of the expressions whose score is determined by fp64 arithmetic: the oracle is run
     again `probes` times with every transcendental result moved by a random +-1 ulp (other, equally valid
@@ -180,12 +187,14 @@ def score_discrepancy_explained(expr, xs, ys, max_leafs, got, want, sum_mode=SUM
     test is not reproducible this way, so it still fails."""
     need = 0.5 * abs(got - want)
     try:
+        lib().oracle_set_jitter_ulps(EXPLAIN_ULPS)
         for seed in range(1, max_probes + 1):
             lib().oracle_set_jitter(seed)
             if abs(score_fn(expr, xs, ys, max_leafs, sum_mode) - want) >= need:
                 return True
     finally:
         lib().oracle_set_jitter(0)
+        lib().oracle_set_jitter_ulps(1)
     return False
 
 
@@ -196,6 +205,7 @@ def eval_discrepancy_explained(expr, xs, got, want, max_probes=256):
         bad = ~((got == want) | (np.abs(got - want) <= 1e-9 * np.abs(want)))
     todo = set(np.nonzero(bad)[0].tolist())
     try:
+        lib().oracle_set_jitter_ulps(EXPLAIN_ULPS)
         for seed in range(1, max_probes + 1):
             if not todo:
                 break
@@ -210,4 +220,5 @@ def eval_discrepancy_explained(expr, xs, got, want, max_probes=256):
                     todo.discard(k)
     finally:
         lib().oracle_set_jitter(0)
+        lib().oracle_set_jitter_ulps(1)
     return not todo, int(bad.sum())

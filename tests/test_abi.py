@@ -27,6 +27,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"closyr_b200" in L.lib().closyr_version()
 
 
+def test_builder_buffer_falls_back_when_page_locked_memory_runs_out():
+    """a failed page-locked growth must release the old (page-locked) block with the page-locked
+    deallocator, keep the data and continue in pageable memory."""
+    lib = C.CDLL(L.SO_PATH)
+    lib.closyr_selftest_pinned_fallback.restype = C.c_int
+    assert lib.closyr_selftest_pinned_fallback() == 0
+
+
 def test_header_cites_reference_interfaces():
     text = open(os.path.join(ROOT, "include", "closyr_b200.h")).read()
     for cite in ("src/closyr/ops.clj:119-136", "src/closyr/ops/eval.clj:99-112", "src/closyr/symbolic_regression.clj:474-478",
