@@ -215,6 +215,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.rflags = (uint8_t *)d.rflags.p;
     sp.partials = nullptr;
     sp.partial_tile_offset = 0;
+    if (ne * n_tiles > 0x7fffffff) return fail(ctx, CLOSYR_E_ARG, "too many (expression, tile) items for one launch");
     const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts, cpt, score_warps(cpt));
     const bool direct = want_final && n_tiles == 1;
     sp.final_scores = direct ? 1 : 0;

@@ -9,6 +9,7 @@
 // over the 128-point chunks) so a score is bit-identical for every tiling, sharding and GPU count.  The epilogue reproduces
 // closyr's formula operation by operation (reference src/closyr/ops.clj:78-116); the file is compiled with
 // -fmad=false so none of it is contracted.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
@@ -116,8 +117,8 @@ __device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_
     return finish_stage(L, ncode, smem, tid, nthreads, nullptr, 0, s_pflags);
 }
 
-// One round of a CTA = one 128-point chunk per warp: v[j] = f(x[j]) for the lane's 4 points, nr = mask of points
-// whose value is not a real number (eval.clj:70-80 turns those into +Inf).
+// One round of a CTA = one 128-point chunk per warp: v[j] = f(x[j]) for the lane's 4 points (+Inf where the value is
+// not a real number, as eval.clj:70-80 has it), nr = mask of those points.
 //
 // Every warp first runs the IEEE-real fast path on its chunk.  The points it reports are compacted across
 // the WHOLE CTA into one list and re-evaluated with the complete algebra, 64 points (2 per lane) per warp and
@@ -132,32 +133,20 @@ struct Round {
 };
 constexpr int CPLX_POINTS = 2;       // points per lane of the complete-algebra interpreter
 
-__device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bool active, bool is_const, bool quirk,
-                                           uint32_t quirk_off, int64_t base, int64_t n, const double *__restrict__ xs,
-                                           double (&v)[4], uint32_t &valid, uint32_t &nr, uint32_t &mode,
-                                           uint32_t round_parity)
+struct CplxPassResult { double v[4]; uint32_t nr, mode; };
+
+// The cold half of a round: some point of the CTA was reported.  A function of its own so that the state it needs
+// does not live in the registers of the common path.
+__device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ sconst, const uint32_t tcode_addr,
+                                                 const uint32_t slot_addr, const double *__restrict__ leaf_tab,
+                                                 double *__restrict__ list, uint32_t *__restrict__ cnt,
+                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev,
+                                                 const double v0, const double v1, const double v2, const double v3)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    valid = 0;
-    nr = 0;
-    uint32_t ev = 0;
-    if (active) {
-        // xs (and every table row) is padded to whole chunks with x = 1.0, so a lane always loads its 4 points
-        const int64_t left = n - base;
-        valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
-        if (quirk) {
-            // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
-#pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? st.sconst[quirk_off + base + j] : 0.0;
-        } else if (mode == 0 && !is_const && !(st.pflags & PF_NO_FAST)) {
-            const RealResult<4> rr = run_real<4>(st.tcode_addr, st.slot_addr, xs + base, st.leaf_tab ? st.leaf_tab + base : nullptr);
-#pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = rr.v[j];
-            ev = rr.ev & valid;
-        } else ev = valid;
-    }
-    // nothing reported anywhere in the CTA (the common round): one barrier, no compaction
-    if (!__syncthreads_or(ev != 0)) return false;
+    CplxPassResult res;
+    res.v[0] = v0; res.v[1] = v1; res.v[2] = v2; res.v[3] = v3;
+    res.nr = 0;
     // CTA-wide compaction of the reported points
     const uint32_t mine = __popc(ev);
     uint32_t incl = mine;
@@ -166,7 +155,6 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
         const uint32_t t = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += t;
     }
-    uint32_t *cnt = rd.counts + round_parity * 32;
     if (lane == 31) cnt[warp] = incl;
     __syncthreads();
     uint32_t cw = lane < nwarps ? cnt[lane] : 0u, ci = cw;
@@ -179,7 +167,7 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
     uint32_t pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if ((ev >> j) & 1u) rd.list[pos++] = __longlong_as_double(base + j);      // the point's index
+        if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
     __syncthreads();
     constexpr uint32_t TASK = 32 * CPLX_POINTS;
     for (uint32_t t0 = warp * TASK; t0 < total; t0 += nwarps * TASK) {
@@ -187,14 +175,14 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
             const uint32_t r = t0 + j * 32 + lane;
-            ca.idx[j] = __double_as_longlong(rd.list[r < total ? r : t0]);       // idle lanes repeat the task's first point
+            ca.idx[j] = __double_as_longlong(list[r < total ? r : t0]);          // idle lanes repeat the task's first point
         }
-        const CplxResult<CPLX_POINTS> cr = run_cplx<CPLX_POINTS>(st.tcode_addr, st.slot_addr, st.sconst, xs, ca, st.leaf_tab);
+        const CplxResult<CPLX_POINTS> cr = run_cplx<CPLX_POINTS>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
             const uint32_t r = t0 + j * 32 + lane;
-            if (r < total) rd.list[r] = ((cr.nonreal >> j) & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : cr.out[j];   // NaN marks "not a real number"
+            if (r < total) list[r] = ((cr.nonreal >> j) & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : cr.out[j];   // NaN marks "not a real number"
         }
     }
     __syncthreads();
@@ -202,16 +190,50 @@ __device__ __forceinline__ bool eval_round(const Staged &st, const Round &rd, bo
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if ((ev >> j) & 1u) {
-            const double r = rd.list[pos++];
-            if (r != r) { v[j] = 0.0; nr |= 1u << j; }
-            else v[j] = r;
+            const double r = list[pos++];
+            if (r != r) { res.v[j] = __longlong_as_double(0x7ff0000000000000ll); res.nr |= 1u << j; }
+            else res.v[j] = r;
         }
     }
-    mode = (total * 4u >= (uint32_t)blockDim.x * 4u * 3u) ? 1u : 0u;      // >= 75 % of the round's points
-    return mine != 0;
+    res.mode = (total * 4u >= (uint32_t)blockDim.x * 4u * 3u) ? 1u : 0u;      // >= 75 % of the round's points
+    return res;
 }
 
-// ---- TMA bulk staging (cp.async.bulk + mbarrier): the population buffer is laid out for it (every program and
+// The slow half of a round, for one warp: called by every warp of the CTA when any point of the round was reported (or
+// when the round has no fast pass at all).  Compaction + complete algebra (cplx_pass), then the chunk's residuals again
+// from the merged values.  ev = this lane's points that need the complete algebra, v = the fast pass' values of the
+// others.  A function of its own: the common path of the kernel keeps none of this state in registers.
+struct RoundSlowResult { double v[4]; double mx; uint32_t nr, mode, used; };
+
+__device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sconst, const uint32_t tcode_addr,
+                                                   const uint32_t slot_addr, const double *__restrict__ leaf_tab,
+                                                   double *__restrict__ list, uint32_t *__restrict__ cnt,
+                                                   const double *__restrict__ xs, const double *__restrict__ ys,
+                                                   const int64_t base, const uint32_t valid, const uint32_t ev_in,
+                                                   const uint32_t quirk_off_plus1, const uint32_t sum_addr,
+                                                   const double v0, const double v1, const double v2, const double v3)
+{
+    RoundSlowResult out;
+    uint32_t ev = ev_in;
+    double v[4] = { v0, v1, v2, v3 };
+    if (quirk_off_plus1) {
+        // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
+        ev = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? sconst[quirk_off_plus1 - 1 + base + j] : 0.0;
+    }
+    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, list, cnt, xs, base, ev, v[0], v[1], v[2], v[3]);
+    out.nr = cp.nr;
+    out.mode = cp.mode;
+    out.used = __any_sync(FULL, ev != 0) ? 1u : 0u;
+    out.mx = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) out.v[j] = cp.v[j];
+    if (__any_sync(FULL, valid != 0)) out.mx = chunk_residuals(cp.v, ys + base, valid, sum_addr);      // not for an idle warp
+    return out;
+}
+
+// ---- TMA bulk copies (cp.async.bulk + mbarrier): the population buffer is laid out for it (every program and
 // every constant pool starts on a 16-byte boundary and is a multiple of 16 bytes long)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
@@ -238,6 +260,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// largest of a warp's non-negative doubles: their bit patterns order like their values
+__device__ __forceinline__ double warp_max_nonneg(double m)
+{
+    const uint32_t hi = (uint32_t)__double2hiint(m);
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? (uint32_t)__double2loint(m) : 0u);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 // stages one program with two TMA bulk copies and translates it; every thread of the CTA calls it, thread 0 issues
@@ -306,41 +337,40 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     const int cnt = (int)(c_hi - c_lo);
 
     __shared__ uint32_t s_counts[64];
-    const Round rd = { st.slvl + p.chunks_per_tile, s_counts };
+    double *const list = st.slvl + p.chunks_per_tile;
+    const uint32_t slvl_addr = smem_u32(st.slvl);
+    const bool fast_ok = !is_const && !(st.pflags & PF_NO_FAST);
     double warp_mx = 0.0;
-    uint32_t nonreal = 0, mode = 0, parity = 0;
-    bool used_full = false;
+    uint32_t nonreal = 0, mode = 0, parity = 0, used_full = 0;
     for (int64_t c0 = c_lo; c0 < c_hi; c0 += nwarps, parity ^= 1u) {
         const int64_t c = c0 + warp;
-        const bool active = c < c_hi;
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        double v[4], y[4];
-        uint32_t valid, nr;
-        used_full |= eval_round(st, rd, active, is_const, quirk, quirk_off, base, p.n, p.xs, v, valid, nr, mode, parity);
-        if (!active) continue;
-        {                                                      // ys is padded to whole chunks like xs
-            const double2 a = *reinterpret_cast<const double2 *>(p.ys + base);
-            const double2 b = *reinterpret_cast<const double2 *>(p.ys + base + 2);
-            y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
+        // xs, ys and every table row are padded to whole chunks (x = 1.0, y = 0.0), so a lane always loads its 4 points
+        const int64_t left = c < c_hi ? p.n - base : 0;
+        const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
+        const uint32_t sum_addr = slvl_addr + (uint32_t)(c - c_lo) * 8u;
+        const bool fast = fast_ok && mode == 0;
+        RealResult<4> rr;
+        rr.ev = valid;
+        rr.mx = 0.0;
+        rr.v[0] = rr.v[1] = rr.v[2] = rr.v[3] = 0.0;
+        if (fast && c < c_hi)
+            rr = run_real<4>(st.tcode_addr, st.slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+        // nothing reported anywhere in the CTA (the common round): one barrier, the fast pass has done everything
+        if (fast && !__syncthreads_or(rr.ev != 0)) {
+            warp_mx = max_nonneg(warp_mx, rr.mx);
+            continue;
         }
-        // compute-residual (ops.clj:78-90): NaN or non-real => max-resid; else min(max-resid, |y - f|)
-        double s = 0.0, m = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double r = fmin(CLOSYR_MAX_RESID, fabs(y[j] - v[j]));
-            if ((nr >> j) & 1u) r = CLOSYR_MAX_RESID;
-            if (!((valid >> j) & 1u)) r = 0.0;
-            s = s + r;
-            m = fmax(m, r);
-        }
-        nonreal += __popc(nr);
-        s = warp_sum(s);
-        warp_mx = fmax(warp_mx, m);
-        if (lane == 0) st.slvl[c - c_lo] = s;                  // the chunk's residual sum, leaf of the tree
+        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, p.leaf_tab, list, s_counts + parity * 32, p.xs, p.ys,
+                                              base, valid, rr.ev, quirk ? quirk_off + 1u : 0u, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
+        warp_mx = max_nonneg(warp_mx, rs.mx);
+        nonreal += __popc(rs.nr);
+        used_full |= rs.used;
+        mode = rs.mode;
     }
-    warp_mx = warp_max(warp_mx);
+    warp_mx = warp_max_nonneg(warp_mx);
     nonreal = __reduce_add_sync(FULL, nonreal);
-    if (lane == 0) { s_max[warp] = warp_mx; s_nonreal[warp] = nonreal; s_full[warp] = used_full ? 1u : 0u; }
+    if (lane == 0) { s_max[warp] = warp_mx; s_nonreal[warp] = nonreal; s_full[warp] = used_full; }
     __syncthreads();
     if (warp != 0) return;
 
@@ -350,7 +380,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         __syncwarp();
     }
     // max, counts and flags of the warps: one lane per warp, then shuffles (all three are order-independent)
-    double tile_max = warp_max(lane < nwarps ? s_max[lane] : 0.0);
+    const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
     const uint32_t tile_nonreal = __reduce_add_sync(FULL, lane < nwarps ? s_nonreal[lane] : 0u);
     const uint32_t tile_full = __reduce_or_sync(FULL, lane < nwarps ? s_full[lane] : 0u);
     if (lane != 0) return;
@@ -441,18 +471,21 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
     const uint32_t quirk_off = aux & 0xffffu;
     const int64_t nchunks = (p.n + CHUNK_POINTS - 1) / CHUNK_POINTS;
     __shared__ uint32_t s_counts[64];
-    const Round rd = { st.slvl, s_counts };
-    uint32_t nonreal = 0, mode = 0;
+    __shared__ double s_sum;                                   // the chunk sums are not used here
+    uint32_t nonreal = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t c = 0; c < nchunks; c++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        double v[4];
-        uint32_t valid, nr;
-        eval_round(st, rd, true, is_const, quirk, quirk_off, base, p.n, p.xs, v, valid, nr, mode, (uint32_t)(c & 1));
-        nonreal += __popc(nr);
+        const int64_t left = p.n - base;
+        const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
+        // every point through the complete algebra (one warp per expression: there is no load to balance, and the
+        // report path evaluates few points); xs doubles as the y vector of the unused residuals
+        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, nullptr, st.slvl, s_counts + (c & 1) * 32, p.xs, p.xs,
+                                              base, valid, valid, quirk ? quirk_off + 1u : 0u, smem_u32(&s_sum), 0.0, 0.0, 0.0, 0.0);
+        nonreal += __popc(rs.nr);
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if ((valid >> j) & 1u) p.out_f[e * p.n + base + j] = ((nr >> j) & 1u) ? inf : v[j];
+            if ((valid >> j) & 1u) p.out_f[e * p.n + base + j] = ((rs.nr >> j) & 1u) ? inf : rs.v[j];
     }
     nonreal = __reduce_add_sync(FULL, nonreal);
     if (lane == 0) p.status[e] = (is_const && !quirk && nonreal != 0) ? 2 : 0;

@@ -630,7 +630,44 @@ template <int P> __device__ __forceinline__ void f_tabulated(uint32_t op, double
 // in C++, the same switch became a compare tree (NVVM has no jump tables) with register copies of the whole
 // accumulator at the loop head: 25 instructions per dispatch.  The block exits for the elementary functions, which
 // C++ handles below, and for END.
-template <int P> struct RealResult { double v[P]; uint32_t ev; };
+// What a warp's fast pass over one 128-point chunk returns: the values, the mask of reported points, and -- computed here
+// because the interpreter's registers are free again at that point, while the calling kernel has none to spare -- the
+// lane's largest residual; the chunk's residual sum goes straight to shared memory (the leaf of the reduction tree).
+template <int P> struct RealResult { double v[P]; double mx; uint32_t ev; };
+
+// residuals (ops.clj:78-90) without FP64 min / max (four instructions each on this chip):
+// a = |y - f| is non-negative or NaN, so its bit pattern orders like its value with NaN on top
+__device__ __forceinline__ double clamp_resid(double a)
+{
+    return ((uint32_t)__double2hiint(a) & 0x7fffffffu) >= 0x412e8480u ? CLOSYR_MAX_RESID : a;     // hi word of 1e6; its lo word is 0
+}
+__device__ __forceinline__ double max_nonneg(double a, double b)
+{
+    return (unsigned long long)__double_as_longlong(a) >= (unsigned long long)__double_as_longlong(b) ? a : b;
+}
+// residuals of a lane's 4 points against y, their left-fold sum reduced over the warp with the fixed xor butterfly and
+// stored by lane 0 at `sum_addr` (shared); returns the lane's largest residual.  Whole warps only.
+__device__ __forceinline__ double chunk_residuals(const double (&v)[4], const double *__restrict__ yp, uint32_t valid,
+                                                  uint32_t sum_addr)
+{
+    double y[4];
+    ldg_x(yp, y);                                          // ys is padded to whole chunks like xs
+    double r0 = clamp_resid(fabs(y[0] - v[0])), r1 = clamp_resid(fabs(y[1] - v[1]));
+    double r2 = clamp_resid(fabs(y[2] - v[2])), r3 = clamp_resid(fabs(y[3] - v[3]));
+    if (valid != 0xfu) {                                   // the run's last chunk
+        if (!(valid & 1u)) r0 = 0.0;
+        if (!(valid & 2u)) r1 = 0.0;
+        if (!(valid & 4u)) r2 = 0.0;
+        if (!(valid & 8u)) r3 = 0.0;
+    }
+    double s = ((r0 + r1) + r2) + r3;                      // lane-local left fold (0.0 + r0 == r0)
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, st);
+    uint32_t lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    if (lane == 0) sts_f64(sum_addr, s);
+    return max_nonneg(max_nonneg(r0, r1), max_nonneg(r2, r3));
+}
 
 // The cheap handlers in PTX.  S = this copy's suffix, T = the other copy's: the loop is unrolled twice so that the
 // entry of the NEXT instruction is already being loaded (into the other copy's registers) while this one runs.
@@ -710,7 +747,8 @@ template <int P> struct RealResult { double v[P]; uint32_t ev; };
 
 template <int P>
 __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const uint32_t slot_addr,
-                                               const double *__restrict__ xp, const double *__restrict__ tab)
+                                               const double *__restrict__ xp, const double *__restrict__ tab,
+                                               const double *__restrict__ yp, const uint32_t valid, const uint32_t sum_addr)
 {
     constexpr uint32_t ALL = (1u << P) - 1u;
     static_assert(P == 4, "slot stride and x loads are written for 4 points per lane");
@@ -748,7 +786,8 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         switch (h) {
         case TH_END: {
             CLOSYR_FORJ if (acc[j] != acc[j]) ev |= 1u << j;
-            res.ev = ev;
+            res.ev = ev & valid;
+            res.mx = chunk_residuals(acc, yp, valid, sum_addr);     // overwritten by the slow path when a point was reported
             return res;
         }
         case TH_TABC: {
@@ -757,7 +796,7 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
             // the warp is lost the rest of the fast pass is wasted work (the complete algebra starts over anyway)
             CLOSYR_PUSH_IF()
             ldg_x(reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c)), acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         }
         case TH_MOD:                                         // PUSH / SRCX modifiers of a function that has no table
@@ -771,12 +810,12 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         case TH_RECIP: ev |= mask_nonfinite<P>(acc); f_recip<P>(acc); break;
         case TH_SQRT:
             f_sqrt<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         case TH_RSQRT:
             ev |= mask_nonfinite<P>(acc);
             f_rsqrt<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         case TH_POWI: {
             const int n = (int)(short)(aux >> 16);
@@ -790,25 +829,25 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         case TH_POWC:
             ev |= mask_nonfinite<P>(acc);
             f_powc<P>(acc, c);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         case TH_EXP: ev |= mask_nonfinite<P>(acc); v_exp<P>(acc); break;
         case TH_LOG:
             v_log<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         case TH_SIN: v_sin<P>(acc); break;
         case TH_COS: v_cos<P>(acc); break;
         case TH_TAN: f_tan<P>(acc); break;
         case TH_ASIN:
             f_asin<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
         case TH_ACOS:
             f_acos<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL; return res; }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
             break;
-        default: { res.ev = ALL; return res; }                 // LDZ LDSPEC POWS: PF_NO_FAST programs do not come here
+        default: { res.ev = ALL & valid; res.mx = 0.0; return res; }                 // LDZ LDSPEC POWS: PF_NO_FAST programs do not come here
         }
     }
 #undef CLOSYR_PUSH_IF
