@@ -138,7 +138,7 @@ struct CplxPassResult { double v[4]; uint32_t nr, mode; };
 // The cold half of a round: some point of the CTA was reported.  A function of its own so that the state it needs
 // does not live in the registers of the common path.
 __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ sconst, const uint32_t tcode_addr,
-                                                 const uint32_t slot_addr, const double *__restrict__ leaf_tab,
+                                                 const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                  double *__restrict__ list, uint32_t *__restrict__ cnt,
                                                  const double *__restrict__ xs, const int64_t base, const uint32_t ev,
                                                  const double v0, const double v1, const double v2, const double v3)
@@ -177,7 +177,8 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
             const uint32_t r = t0 + j * 32 + lane;
             ca.idx[j] = __double_as_longlong(list[r < total ? r : t0]);          // idle lanes repeat the task's first point
         }
-        const CplxResult<CPLX_POINTS> cr = run_cplx<CPLX_POINTS>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
+        const CplxResult<CPLX_POINTS> cr = deep ? run_cplx<CPLX_POINTS, true>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab)
+                                                : run_cplx<CPLX_POINTS, false>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
@@ -206,7 +207,7 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
 struct RoundSlowResult { double v[4]; double mx; uint32_t nr, mode, used; };
 
 __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sconst, const uint32_t tcode_addr,
-                                                   const uint32_t slot_addr, const double *__restrict__ leaf_tab,
+                                                   const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                    double *__restrict__ list, uint32_t *__restrict__ cnt,
                                                    const double *__restrict__ xs, const double *__restrict__ ys,
                                                    const int64_t base, const uint32_t valid, const uint32_t ev_in,
@@ -222,7 +223,7 @@ __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sc
 #pragma unroll
         for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? sconst[quirk_off_plus1 - 1 + base + j] : 0.0;
     }
-    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, list, cnt, xs, base, ev, v[0], v[1], v[2], v[3]);
+    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, deep, list, cnt, xs, base, ev, v[0], v[1], v[2], v[3]);
     out.nr = cp.nr;
     out.mode = cp.mode;
     out.used = __any_sync(FULL, ev != 0) ? 1u : 0u;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
             warp_mx = max_nonneg(warp_mx, rr.mx);
             continue;
         }
-        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, p.leaf_tab, list, s_counts + parity * 32, p.xs, p.ys,
+        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, p.leaf_tab, (st.pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
                                               base, valid, rr.ev, quirk ? quirk_off + 1u : 0u, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
         nonreal += __popc(rs.nr);
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
         const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
         // every point through the complete algebra (one warp per expression: there is no load to balance, and the
         // report path evaluates few points); xs doubles as the y vector of the unused residuals
-        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, nullptr, st.slvl, s_counts + (c & 1) * 32, p.xs, p.xs,
+        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, nullptr, (st.pflags & PF_DEEP) != 0, st.slvl, s_counts + (c & 1) * 32, p.xs, p.xs,
                                               base, valid, valid, quirk ? quirk_off + 1u : 0u, smem_u32(&s_sum), 0.0, 0.0, 0.0, 0.0);
         nonreal += __popc(rs.nr);
 #pragma unroll

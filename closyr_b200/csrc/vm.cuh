@@ -429,11 +429,12 @@ __device__ __noinline__ Z zpow(Z z, Z w)
 struct __align__(16) TInsn { uint32_t h, aux; double c; };
 
 enum {
-    // the "cheap" handlers, 0 .. TH_CHEAP - 1: run_real interprets them inside one PTX block (brx.idx dispatch).
+    // the "cheap" handlers, 0 .. TH_CHEAP - 1: both interpreters run them inside one PTX block (brx.idx dispatch).
     // The ...P forms store acc to a slot first (ISA v1.1 PUSH); TH_TAB = a tabulated function of the raw variable
-    // that is real everywhere (sin cos exp tan 1/x)
-    TH_END = 0, TH_LDX, TH_LDXP, TH_LDC, TH_LDCP, TH_TAB, TH_TABP, TH_ADDX, TH_ADDC, TH_MULX, TH_MULC, TH_NEG, TH_SQR,
-    TH_ABS, TH_ST, TH_ADDS, TH_MULS,
+    // whose table entry is the algebra's value everywhere (sin cos exp tan); TH_TABR = 1/x (same for the fast path;
+    // the complete algebra must turn the pole into ComplexInfinity)
+    TH_END = 0, TH_LDX, TH_LDXP, TH_LDC, TH_LDCP, TH_TAB, TH_TABP, TH_TABR, TH_TABRP, TH_ADDX, TH_ADDC, TH_MULX, TH_MULC,
+    TH_NEG, TH_SQR, TH_ABS, TH_ST, TH_ADDS, TH_MULS,
     TH_CHEAP,
     // TH_TABC = a tabulated function with a domain (sqrt, x^-1/2, log, asin, acos); TH_MOD = PUSH / SRCX modifiers of
     // a function that has no table, followed by the function itself
@@ -442,7 +443,7 @@ enum {
     TH_LDZ, TH_LDSPEC, TH_POWS,
     TH_COUNT
 };
-static_assert(TH_CHEAP == 17 && TH_COUNT == 34, "the branch-target table in run_real lists the handlers by position");
+static_assert(TH_CHEAP == 19 && TH_COUNT == 36, "the branch-target tables of the interpreters list the handlers by position");
 // program properties found while decoding
 constexpr uint32_t PF_NO_FAST = 1u;   // an instruction the IEEE fast path cannot express: every point takes run_cplx
 constexpr uint32_t PF_DEEP = 2u;      // uses spill slots >= CLOSYR_REG_SLOTS (kept in local memory by run_cplx)
@@ -483,8 +484,9 @@ __device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__rest
         }
         if ((a & CL_M_SRCX) && have_tab && op >= CL_RECIP && op <= CL_ACOS && ((VM_TAB_MASK >> (op - CL_RECIP)) & 1u)) {
             // real on the whole line: sin cos exp tan 1/x; with a domain: sqrt x^-1/2 log asin acos
-            const bool total = op == CL_SIN || op == CL_COS || op == CL_EXP || op == CL_TAN || op == CL_RECIP;
-            t.h = total ? ((a & CL_M_PUSH) ? TH_TABP : TH_TAB) : TH_TABC;
+            const bool total = op == CL_SIN || op == CL_COS || op == CL_EXP || op == CL_TAN;
+            const uint32_t push = (a & CL_M_PUSH) ? 1u : 0u;
+            t.h = total ? TH_TAB + push : (op == CL_RECIP ? TH_TABR + push : TH_TABC);
             t.aux = (mods & ~1u) | (f << 2);
             t.c = __longlong_as_double((long long)(op - CL_RECIP) * tab_stride * 8);
         } else if (a & (CL_M_SRCX | CL_M_PUSH)) {
@@ -735,8 +737,8 @@ __device__ __forceinline__ double chunk_residuals(const double (&v)[4], const do
     "NEXT_" S ":\n\t"                                                                          \
     "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%4+16];\n\t"                  \
     "add.u32 %4, %4, 16;\n\t"                                                                  \
-    "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", ADDX_" S ", ADDC_" S \
-    ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S                             \
+    "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", TAB_" S ", TABP_" S \
+    ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S       \
     ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S   \
     ", X_" S ", X_" S ", X_" S ", X_" S ";\n\t"                                                \
     "brx.idx.uni h" S "_, tbl" S "_;\n\t"                                                      \
@@ -953,7 +955,67 @@ __device__ __noinline__ Z zrsqrt(Z a) { return zrecip(zsqrt(a)); }
 template <int P> struct CplxArgs { int64_t idx[P]; };
 template <int P> struct CplxResult { double out[P]; uint32_t nonreal; };
 
-template <int P>
+// The cheap handlers of REAL MODE in PTX, two points per lane (the structure of run_real's block; see there).
+// Operands: %0 %1 the real parts, %2 ip, %3 sm (bit k = slot k holds imaginary parts), %4..%7 = h aux c.lo c.hi of the
+// instruction the block exits on, %8 this lane's slot column, %9 %10 x, %11 %12 this lane's two columns of the tables.
+// A slot operand with imaginary parts, the 1/x table (pole) and everything that is not cheap leave the block.
+#define CLOSYR_PUSH2_PTX(S)                      \
+    "bfe.u32 t_, aux" S "_, 10, 2;\n\t"          \
+    "bfi.b32 %3, z_, %3, t_, 1;\n\t"             \
+    "and.b32 t_, aux" S "_, 0xc00;\n\t"          \
+    "add.u32 t_, t_, %8;\n\t"                    \
+    "st.shared.f64 [t_], %0;\n\t"                \
+    "st.shared.f64 [t_+256], %1;\n\t"
+#define CLOSYR_OP2(OP, B0, B1) OP " %0, %0, " B0 ";\n\t" OP " %1, %1, " B1 ";\n\t"
+#define CLOSYR_SLOT_REAL_OR_EXIT(S)              \
+    "shr.u32 t_, aux" S "_, 10;\n\t"             \
+    "shr.u32 t_, %3, t_;\n\t"                    \
+    "and.b32 t_, t_, 1;\n\t"                     \
+    "setp.ne.u32 p_, t_, 0;\n\t"                 \
+    "@p_ bra.uni X_" S ";\n\t"                   \
+    "add.u32 t_, aux" S "_, %8;\n\t"             \
+    "ld.shared.f64 s0_, [t_];\n\t ld.shared.f64 s1_, [t_+256];\n\t"
+#define CLOSYR_CHEAP2_HANDLERS(S, T)                                                           \
+    "LDXP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
+    "LDX_" S ":\n\t mov.f64 %0, %9;\n\t mov.f64 %1, %10;\n\t bra.uni NEXT_" T ";\n\t"          \
+    "LDCP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
+    "LDC_" S ":\n\t mov.b64 %0, {lo" S "_, hi" S "_};\n\t mov.f64 %1, %0;\n\t bra.uni NEXT_" T ";\n\t" \
+    "TABP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
+    "TAB_" S ":\n\t"                                                                           \
+    "mov.b64 ad_, {lo" S "_, hi" S "_};\n\t"                                                   \
+    "add.s64 a0_, ad_, %11;\n\t add.s64 a1_, ad_, %12;\n\t"                                    \
+    "ld.global.nc.f64 %0, [a0_];\n\t ld.global.nc.f64 %1, [a1_];\n\t"                          \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "ADDX_" S ":\n\t" CLOSYR_OP2("add.rn.f64", "%9", "%10") "bra.uni NEXT_" T ";\n\t"          \
+    "MULX_" S ":\n\t" CLOSYR_OP2("mul.rn.f64", "%9", "%10") "bra.uni NEXT_" T ";\n\t"          \
+    "ADDC_" S ":\n\t mov.b64 c_, {lo" S "_, hi" S "_};\n\t" CLOSYR_OP2("add.rn.f64", "c_", "c_") "bra.uni NEXT_" T ";\n\t" \
+    "MULC_" S ":\n\t mov.b64 c_, {lo" S "_, hi" S "_};\n\t" CLOSYR_OP2("mul.rn.f64", "c_", "c_") "bra.uni NEXT_" T ";\n\t" \
+    "NEG_" S ":\n\t neg.f64 %0, %0;\n\t neg.f64 %1, %1;\n\t bra.uni NEXT_" T ";\n\t"           \
+    "SQR_" S ":\n\t" CLOSYR_OP2("mul.rn.f64", "%0", "%1") "bra.uni NEXT_" T ";\n\t"            \
+    "ABS_" S ":\n\t abs.f64 %0, %0;\n\t abs.f64 %1, %1;\n\t bra.uni NEXT_" T ";\n\t"           \
+    "ST_" S ":\n\t"                                                                            \
+    "shr.u32 t_, aux" S "_, 10;\n\t"                                                           \
+    "bfi.b32 %3, z_, %3, t_, 1;\n\t"                                                           \
+    "add.u32 t_, aux" S "_, %8;\n\t"                                                           \
+    "st.shared.f64 [t_], %0;\n\t st.shared.f64 [t_+256], %1;\n\t"                              \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    "ADDS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("add.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
+    "MULS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("mul.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
+    "NEXT_" S ":\n\t"                                                                          \
+    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%2+16];\n\t"                  \
+    "add.u32 %2, %2, 16;\n\t"                                                                  \
+    "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", X_" S ", X_" S \
+    ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S      \
+    ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S   \
+    ", X_" S ", X_" S ", X_" S ", X_" S ";\n\t"                                                \
+    "brx.idx.uni h" S "_, tbl" S "_;\n\t"                                                      \
+    "X_" S ":\n\t"                                                                             \
+    "mov.b32 %4, h" S "_;\n\t mov.b32 %5, aux" S "_;\n\t mov.b32 %6, lo" S "_;\n\t mov.b32 %7, hi" S "_;\n\t" \
+    "bra.uni OUT_;\n\t"
+
+// DEEP = the program uses spill slots >= CLOSYR_REG_SLOTS (PF_DEEP): those live in local memory and the PTX block is
+// not used.  Ordinary programs take the other instantiation, which has neither.
+template <int P, bool DEEP>
 __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const uint32_t slot_addr,
                                                const double *__restrict__ sconst, const double *__restrict__ xs,
                                                const CplxArgs<P> args, const double *__restrict__ tab)
@@ -962,36 +1024,38 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
     constexpr unsigned FULLW = 0xffffffffu;
     constexpr uint32_t SLOT_SHIFT = 10;                     // 1 KiB per slot, as run_real<4>: [re|im][P points][32 lanes]
     constexpr uint32_t IM_OFF = 512;
-    static_assert(P == 2, "slot layout is written for 2 points per lane");
+    constexpr int NDEEP = DEEP ? CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS : 1;
+    static_assert(P == 2, "slot layout and the PTX block are written for 2 points per lane");
     CAcc<P> a;
-    Z deep[CLOSYR_MAX_SLOTS - CLOSYR_REG_SLOTS][P];         // local memory, touched by PF_DEEP programs only
+    Z deep[NDEEP][P];                                        // local memory (DEEP only)
     uint32_t cmo = 0;                                        // 0 real mode, TH_COUNT complex mode
     uint32_t sm = 0;                                         // slots holding imaginary parts
     uint32_t ip = tcode_addr;
-    uint4 nx = lds_insn(ip);
-    CLOSYR_FORJ { a.re[j] = 0.0; a.im[j] = 0.0; }
+    double x[P];
+    CLOSYR_FORJ { x[j] = ldg_f64(xs + idx[j]); a.re[j] = 0.0; a.im[j] = 0.0; }
+    const double *const tp0 = tab + idx[0], *const tp1 = tab + idx[1];      // never dereferenced without tables
 #define CLOSYR_TO_COMPLEX() { CLOSYR_FORJ a.im[j] = 0.0; cmo = TH_COUNT; }
 #define CLOSYR_STORE(k_)                                                                    \
     {                                                                                       \
         const uint32_t k = (k_);                                                            \
-        if (k < CLOSYR_REG_SLOTS) {                                                         \
+        if (!DEEP || k < CLOSYR_REG_SLOTS) {                                                \
             const uint32_t sl_ = slot_addr + (k << SLOT_SHIFT);                             \
             CLOSYR_FORJ sts_f64(sl_ + j * 256, a.re[j]);                                    \
             if (cmo) { CLOSYR_FORJ sts_f64(sl_ + IM_OFF + j * 256, a.im[j]); sm |= 1u << k; } \
             else sm &= ~(1u << k);                                                          \
         } else {                                                                            \
-            CLOSYR_FORJ deep[k - CLOSYR_REG_SLOTS][j] = zv(a.re[j], cmo ? a.im[j] : 0.0);   \
+            CLOSYR_FORJ deep[DEEP ? k - CLOSYR_REG_SLOTS : 0][j] = zv(a.re[j], cmo ? a.im[j] : 0.0); \
         }                                                                                   \
     }
-#define CLOSYR_PUSH_IF() if (aux & 2u) CLOSYR_STORE((opaque(aux) >> 10) & 3u)
-#define CLOSYR_LOADX(dst) CLOSYR_FORJ dst[j] = ldg_f64(xs + idx[j]);
+#define CLOSYR_PUSH_IF() if (aux & 2u) CLOSYR_STORE((aux >> 10) & 3u)
+#define CLOSYR_LOADX(dst) CLOSYR_FORJ dst[j] = x[j];
     // loads slot k into (sre, sim); `scx` = the slot may hold imaginary parts
 #define CLOSYR_LOAD(k_)                                                                     \
     double sre[P], sim[P];                                                                  \
     bool scx;                                                                               \
     {                                                                                       \
         const uint32_t k = (k_);                                                            \
-        if (k < CLOSYR_REG_SLOTS) {                                                         \
+        if (!DEEP || k < CLOSYR_REG_SLOTS) {                                                \
             const uint32_t sl_ = slot_addr + (k << SLOT_SHIFT);                             \
             scx = (sm >> k) & 1u;                                                           \
             CLOSYR_FORJ sre[j] = lds_f64(sl_ + j * 256);                                    \
@@ -999,7 +1063,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             else { CLOSYR_FORJ sim[j] = 0.0; }                                              \
         } else {                                                                            \
             scx = true;                                                                     \
-            CLOSYR_FORJ { sre[j] = deep[k - CLOSYR_REG_SLOTS][j].re; sim[j] = deep[k - CLOSYR_REG_SLOTS][j].im; } \
+            CLOSYR_FORJ { sre[j] = deep[DEEP ? k - CLOSYR_REG_SLOTS : 0][j].re; sim[j] = deep[DEEP ? k - CLOSYR_REG_SLOTS : 0][j].im; } \
         }                                                                                   \
     }
     // real-mode elementary function: `cond` (per point, on x_ = a.re[j]) says the real routine is the algebra's value
@@ -1014,11 +1078,33 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
     }
 #pragma unroll 1
     for (;;) {
-        uint32_t h = nx.x + cmo;
-        const uint32_t aux = nx.y;
-        const double c = __hiloint2double((int)nx.w, (int)nx.z);
-        ip += 16;
-        nx = lds_insn(ip);
+        uint32_t h, aux, clo, chi;
+        if (!DEEP && cmo == 0) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p_;\n\t"
+                ".reg .b32 t_, z_, hA_, auxA_, loA_, hiA_, hB_, auxB_, loB_, hiB_;\n\t"
+                ".reg .b64 ad_, a0_, a1_;\n\t"
+                ".reg .f64 c_, s0_, s1_;\n\t"
+                "mov.b32 z_, 0;\n\t"
+                "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%2];\n\t"
+                "bra.uni NEXT_A;\n\t"
+                CLOSYR_CHEAP2_HANDLERS("A", "B")
+                CLOSYR_CHEAP2_HANDLERS("B", "A")
+                "OUT_:\n\t"
+                "}\n"
+                : "+d"(a.re[0]), "+d"(a.re[1]), "+r"(ip), "+r"(sm), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
+                : "r"(slot_addr), "d"(x[0]), "d"(x[1]), "l"(tp0), "l"(tp1)
+                : "memory");
+        } else {
+            const uint4 nx = lds_insn(ip);
+            h = nx.x + cmo;
+            aux = nx.y;
+            clo = nx.z;
+            chi = nx.w;
+            ip += 16;
+        }
+        const double c = __hiloint2double((int)chi, (int)clo);
     redo:
         switch (h) {
         case TH_END:
@@ -1043,9 +1129,13 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_LDCP + TH_COUNT: CLOSYR_PUSH_IF() CLOSYR_FORJ a.re[j] = c; cmo = 0; break;
         case TH_TAB:
         case TH_TABP:
+        case TH_TABR:
+        case TH_TABRP:
         case TH_TABC:
         case TH_TAB + TH_COUNT:
         case TH_TABP + TH_COUNT:
+        case TH_TABR + TH_COUNT:
+        case TH_TABRP + TH_COUNT:
         case TH_TABC + TH_COUNT: {
             CLOSYR_PUSH_IF()
             const double *row = reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c));
@@ -1081,19 +1171,19 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             break;
         }
         // ---- real mode: IEEE arithmetic is the algebra
-        case TH_ADDX: { double x[P]; CLOSYR_LOADX(x) CLOSYR_FORJ a.re[j] = a.re[j] + x[j]; break; }
+        case TH_ADDX: CLOSYR_FORJ a.re[j] = a.re[j] + x[j]; break;
         case TH_ADDC: CLOSYR_FORJ a.re[j] = a.re[j] + c; break;
-        case TH_MULX: { double x[P]; CLOSYR_LOADX(x) CLOSYR_FORJ a.re[j] = a.re[j] * x[j]; break; }
+        case TH_MULX: CLOSYR_FORJ a.re[j] = a.re[j] * x[j]; break;
         case TH_MULC: CLOSYR_FORJ a.re[j] = a.re[j] * c; break;
         case TH_NEG: CLOSYR_FORJ a.re[j] = -a.re[j]; break;
         case TH_SQR: CLOSYR_FORJ a.re[j] = a.re[j] * a.re[j]; break;
         case TH_ABS: CLOSYR_FORJ a.re[j] = fabs(a.re[j]); break;
         case TH_ST:
-        case TH_ST + TH_COUNT: CLOSYR_STORE(opaque(aux) >> 10) break;
+        case TH_ST + TH_COUNT: CLOSYR_STORE(aux >> 10) break;
         case TH_ADDS:
         case TH_MULS: {
-            const uint32_t k = opaque(aux) >> 10;
-            const bool scx = k >= CLOSYR_REG_SLOTS || ((sm >> k) & 1u);
+            const uint32_t k = aux >> 10;
+            const bool scx = (DEEP && k >= CLOSYR_REG_SLOTS) || ((sm >> k) & 1u);
             if (scx) {
                 CLOSYR_TO_COMPLEX()
                 h += TH_COUNT;
@@ -1130,17 +1220,17 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_ACOS: CLOSYR_REALF(!(fabs(x_) > 1.0), f_acos<P>(a.re))
         case TH_POWS: CLOSYR_TO_COMPLEX() h += TH_COUNT; goto redo;
         // ---- complex mode
-        case TH_ADDX + TH_COUNT: { double x[P], zr[P]; CLOSYR_LOADX(x) CLOSYR_FORJ zr[j] = 0.0; c_add<P>(a, x, zr); break; }
-        case TH_MULX + TH_COUNT: { double x[P], zr[P]; CLOSYR_LOADX(x) CLOSYR_FORJ zr[j] = 0.0; c_mul<P>(a, x, zr); break; }
+        case TH_ADDX + TH_COUNT: { double zr[P]; CLOSYR_FORJ zr[j] = 0.0; c_add<P>(a, x, zr); break; }
+        case TH_MULX + TH_COUNT: { double zr[P]; CLOSYR_FORJ zr[j] = 0.0; c_mul<P>(a, x, zr); break; }
         case TH_ADDC + TH_COUNT: { double cr[P], zr[P]; CLOSYR_FORJ { cr[j] = c; zr[j] = 0.0; } c_add<P>(a, cr, zr); break; }
         case TH_MULC + TH_COUNT: { double cr[P], zr[P]; CLOSYR_FORJ { cr[j] = c; zr[j] = 0.0; } c_mul<P>(a, cr, zr); break; }
         case TH_NEG + TH_COUNT: CLOSYR_ZCALL(zneg) break;
         case TH_SQR + TH_COUNT: { double sr[P], si[P]; CLOSYR_FORJ { sr[j] = a.re[j]; si[j] = a.im[j]; } c_mul<P>(a, sr, si); break; }
         case TH_ABS + TH_COUNT: CLOSYR_ZCALL(zabs) break;
-        case TH_ADDS + TH_COUNT: { CLOSYR_LOAD(opaque(aux) >> 10) (void)scx; c_add<P>(a, sre, sim); break; }
-        case TH_MULS + TH_COUNT: { CLOSYR_LOAD(opaque(aux) >> 10) (void)scx; c_mul<P>(a, sre, sim); break; }
+        case TH_ADDS + TH_COUNT: { CLOSYR_LOAD(aux >> 10) (void)scx; c_add<P>(a, sre, sim); break; }
+        case TH_MULS + TH_COUNT: { CLOSYR_LOAD(aux >> 10) (void)scx; c_mul<P>(a, sre, sim); break; }
         case TH_POWS + TH_COUNT: {
-            CLOSYR_LOAD(opaque(aux) >> 10)
+            CLOSYR_LOAD(aux >> 10)
             (void)scx;
             CLOSYR_FORJ {
                 const Z r = zpow(zv(sre[j], sim[j]), zv(a.re[j], a.im[j]));
@@ -1191,6 +1281,10 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
 #undef CLOSYR_STORE
 #undef CLOSYR_TO_COMPLEX
 }
+#undef CLOSYR_CHEAP2_HANDLERS
+#undef CLOSYR_SLOT_REAL_OR_EXIT
+#undef CLOSYR_OP2
+#undef CLOSYR_PUSH2_PTX
 #undef CLOSYR_ZCALL
 
 }  // namespace dev

@@ -282,6 +282,38 @@ def test_semantic_cases_match_oracle(ctx):
     check_eval_against_oracle(SEMANTIC_CASES, xs, f, status)
 
 
+def balanced_tree(depth, leaf):
+    """A complete binary tree of alternating Plus / Times: both operands of every node need the same number of spill
+    slots, so the compiler runs out of the four register slots at depth 5 (ISA: CL_ST / CL_ADDS / CL_MULS with a >= 4)."""
+    k = [0]
+
+    def gen(d):
+        if d == 0:
+            k[0] += 1
+            return leaf(k[0])
+        return "%s(%s,%s)" % ("Plus" if d % 2 else "Times", gen(d - 1), gen(d - 1))
+
+    return gen(depth)
+
+
+def test_programs_with_deep_spill_slots(ctx):
+    """Spill slots beyond the four fast ones (local memory in the complete-algebra interpreter, no fast pass)."""
+    texts = [
+        balanced_tree(6, lambda i: "%s(Plus(%d,x))" % (["Sin", "Cos"][i % 2], i)),                      # real everywhere
+        balanced_tree(6, lambda i: "Power(Plus(%d,Times(-1,x)),Rational(1,2))" % (i % 9)),              # complex beyond x = i
+        balanced_tree(5, lambda i: ["Log(x)", "Power(x,-1)", "ArcSin(x)", "Sin(x)"][i % 4]),            # poles, branch cuts
+    ]
+    b = cb.PopulationBuilder()
+    b.add_many(texts)
+    assert ((b.arrays()["meta"] >> 24) > 4).all()
+    xs, ys = synth_points(700)
+    got, flags = gpu_scores(ctx, texts, xs, ys, 1000)
+    want, _ = O.score_batch(texts, xs, ys, 1000)
+    assert_scores_close(got, want, texts)
+    f, status = ctx.eval_batch(b.view(), xs[:200])
+    check_eval_against_oracle(texts, xs[:200], f, status)
+
+
 def test_scores_are_identical_for_every_tiling(ctx):
     """The reduction tree is fixed: a small population (many tiles per expression, partials + finalize kernel)
     and the same expressions inside a large population (one tile per expression) give bit-identical scores."""
