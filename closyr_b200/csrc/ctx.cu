@@ -55,8 +55,10 @@ struct DevBuf {                       // grow-only device allocation
 
 struct DevPop {                       // one resident population shard
     DevBuf code, code_off, consts, const_off, meta, aux;
+    DevBuf tcode, desc;               // what prepare_kernel derives from the arrays above (threaded code, descriptors)
+    int64_t prepared_stride = -2;     // leaf_stride the threaded code was made for (-1: without tables, -2: not made yet)
     int64_t lo = 0, hi = 0;           // expression range of the caller's population held here
-    uint32_t code_base = 0, const_base = 0, max_code = 0, max_consts = 0;
+    uint32_t code_base = 0, const_base = 0, max_code = 0, max_consts = 0, n_words = 0;
     DevPopulation view() const
     {
         DevPopulation v;
@@ -69,9 +71,11 @@ struct DevPop {                       // one resident population shard
         v.code_base = code_base;
         v.const_base = const_base;
         v.n_expr = hi - lo;
+        v.tcode = (const uint4 *)tcode.p;
+        v.desc = (const ExprDesc *)desc.p;
         return v;
     }
-    void release() { code.release(); code_off.release(); consts.release(); const_off.release(); meta.release(); aux.release(); }
+    void release() { code.release(); code_off.release(); consts.release(); const_off.release(); meta.release(); aux.release(); tcode.release(); desc.release(); }
 };
 
 struct DeviceState {
@@ -79,6 +83,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     DevBuf xs, ys, leaf_tab, scores, rflags, partials, partials_all, flush, eval_xs, eval_f, eval_status, rank_a, rank_b;
+    DevBuf csum, cmax, worklist;          // hand-over between the two scoring kernels (kernels.cuh ScoreParams)
     int64_t leaf_stride = 0;
     DevPop pop, eval_pop;
     int64_t chunk_lo = 0, chunk_hi = 0;   // point-sharded mode: this device's chunk range
@@ -125,6 +130,7 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     CU(ctx, cudaSetDevice(d.device));
     dp.lo = lo;
     dp.hi = hi;
+    dp.prepared_stride = -2;
     const int64_t ne = hi - lo;
     if (ne <= 0) return CLOSYR_OK;
     dp.code_base = pop->code_off[lo];
@@ -153,6 +159,7 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
         return fail(ctx, CLOSYR_E_ARG, "population holds a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS");
     dp.max_code = mc;
     dp.max_consts = mk;
+    dp.n_words = (uint32_t)ncode;
     CU(ctx, dp.code.reserve(ncode * 4 + 16));
     CU(ctx, dp.consts.reserve(nk * 8 + 16));
     CU(ctx, dp.code_off.reserve((ne + 1) * 4));
@@ -165,6 +172,27 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     CU(ctx, cudaMemcpyAsync(dp.const_off.p, pop->const_off + lo, (ne + 1) * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.meta.p, pop->meta + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.aux.p, pop->aux + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
+    return CLOSYR_OK;
+}
+
+// threaded code + descriptors of a resident shard (kernels.cu prepare_kernel), made once per upload and again when the
+// leaf tables it refers to change.  leaf_stride < 0: no tables (ad hoc xs).
+int prepare_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, int64_t leaf_stride)
+{
+    const int64_t want = leaf_stride > 0 ? leaf_stride : -1;
+    if (dp.prepared_stride == want || dp.hi <= dp.lo) return CLOSYR_OK;
+    CU(ctx, dp.tcode.reserve((size_t)dp.n_words * 16 + 16));
+    CU(ctx, dp.desc.reserve((size_t)(dp.hi - dp.lo) * sizeof(ExprDesc)));
+    PrepareParams pp;
+    pp.pop = dp.view();
+    pp.tcode = (uint4 *)dp.tcode.p;
+    pp.desc = (ExprDesc *)dp.desc.p;
+    pp.have_tab = want > 0 ? 1 : 0;
+    pp.leaf_stride = want > 0 ? want : 0;
+    launch_prepare(pp, d.stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    dp.prepared_stride = want;
     return CLOSYR_OK;
 }
 
@@ -181,7 +209,7 @@ int check_population(closyr_ctx *ctx, const closyr_population *pop)
 // tile size (in chunks, power of two) so that the launch has enough warps to fill the GPU
 int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
 {
-    const int64_t target_items = 148 * 6;              // CTAs of up to 32 warps, 1 resident per SM, a few waves
+    const int64_t target_items = 148 * 16;             // CTAs of 8 warps, 4 resident per SM, a few waves
     int64_t cpt = pow2_ceil(std::max<int64_t>(1, nchunks));
     while (cpt > MAX_CHUNKS_PER_TILE) cpt >>= 1;
     while (cpt > 4 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;
@@ -193,9 +221,13 @@ int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
 int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_lo, int64_t c_hi, bool want_final,
                  double *partials_out)
 {
+    if (d.pop.hi <= d.pop.lo) return CLOSYR_OK;
+    {
+        int rc = prepare_shard(ctx, d, d.pop, d.leaf_stride);
+        if (rc) return rc;
+    }
     const DevPopulation pv = d.pop.view();
     const int64_t ne = pv.n_expr;
-    if (ne <= 0) return CLOSYR_OK;
     const int64_t nch = c_hi - c_lo;
     const int32_t cpt = pick_chunks_per_tile(ne, nch);
     const int32_t n_tiles = (int32_t)std::max<int64_t>(1, (nch + cpt - 1) / cpt);
@@ -209,6 +241,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.chunk_begin = c_lo;
     sp.chunk_end = c_hi;
     sp.chunks_per_tile = cpt;
+    sp.warps = score_warps(cpt);
     sp.n_tiles = n_tiles;
     sp.max_leafs = max_leafs;
     sp.scores = (double *)d.scores.p;
@@ -216,7 +249,14 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.partials = nullptr;
     sp.partial_tile_offset = 0;
     if (ne * n_tiles > 0x7fffffff) return fail(ctx, CLOSYR_E_ARG, "too many (expression, tile) items for one launch");
-    const size_t smem = score_smem_bytes(d.pop.max_code, d.pop.max_consts, cpt, score_warps(cpt));
+    const size_t n_items = (size_t)ne * n_tiles;
+    CU(ctx, d.csum.reserve(n_items * cpt * 8));
+    CU(ctx, d.cmax.reserve(n_items * 8));
+    CU(ctx, d.worklist.reserve(n_items * 4 + 16));
+    sp.csum = (double *)d.csum.p;
+    sp.cmax = (double *)d.cmax.p;
+    sp.wl_count = (uint32_t *)d.worklist.p;
+    sp.worklist = (uint32_t *)d.worklist.p + 4;
     const bool direct = want_final && n_tiles == 1;
     sp.final_scores = direct ? 1 : 0;
     if (!direct) {
@@ -226,8 +266,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
             sp.partials = (double *)d.partials.p;
         }
     }
-    launch_score(sp, smem, d.stream);
-    ctx->launches++;
+    ctx->launches += launch_score(sp, d.pop.max_code, d.stream);
     CU(ctx, cudaGetLastError());
     if (!direct && !(n_tiles == 1 && partials_out)) {
         FinalizeParams fp;
@@ -310,7 +349,7 @@ void closyr_ctx_destroy(closyr_ctx *ctx)
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.xs, &d.ys, &d.leaf_tab, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
-                           &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b })
+                           &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b, &d.csum, &d.cmax, &d.worklist })
             b->release();
         d.pop.release();
         d.eval_pop.release();
@@ -541,13 +580,15 @@ int closyr_eval_batch(closyr_ctx *ctx, const closyr_population *pop, const doubl
     CU(ctx, d.eval_status.reserve((size_t)ne));
     if (n) CU(ctx, cudaMemcpyAsync(d.eval_xs.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
     if (padded > n) CU(ctx, cudaMemcpyAsync((double *)d.eval_xs.p + n, ones.data(), (size_t)(padded - n) * 8, cudaMemcpyHostToDevice, d.stream));
+    rc = prepare_shard(ctx, d, d.eval_pop, -1);        // ad hoc xs: no leaf tables
+    if (rc) return rc;
     EvalParams ep;
     ep.pop = d.eval_pop.view();
     ep.xs = (const double *)d.eval_xs.p;
     ep.n = n;
     ep.out_f = (double *)d.eval_f.p;
     ep.status = (uint8_t *)d.eval_status.p;
-    launch_eval(ep, score_smem_bytes(d.eval_pop.max_code, d.eval_pop.max_consts, 0, 1), d.stream);
+    launch_eval(ep, eval_smem_bytes(d.eval_pop.max_code), d.stream);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     if (n) CU(ctx, cudaMemcpyAsync(out_f, d.eval_f.p, (size_t)(ne * n) * 8, cudaMemcpyDeviceToHost, d.stream));

@@ -23,7 +23,9 @@ using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_LEVELS = 40;
-constexpr int MAX_SCORE_WARPS = 32;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
+constexpr int FAST_MAX_WARPS = 16;   // score_fast_kernel: warps per CTA (runtime, power of two, default 8)
+constexpr int FAST_MIN_CTAS = 2;     // per SM at the largest CTA: 64 registers per thread
+constexpr int SLOW_WARPS = 32;       // score_slow_kernel: one CTA per SM, one program per SM
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -50,71 +52,183 @@ __device__ __forceinline__ double score_formula(double sum, double mx, int64_t n
 }
 
 struct Staged {
-    const double *sconst;
-    double *slvl;              // per-chunk sums of the tile (score_kernel) / scratch
+    const double *sconst;      // the program's constant pool in global memory (only LDZ and the quirk table read it)
     uint32_t tcode_addr;       // shared-window address of the threaded code (vm.cuh)
     uint32_t slot_addr;        // shared-window address of this lane's column of the warp's spill slots
     uint32_t pflags;           // PF_* properties of the program
     const double *leaf_tab;    // f(x_i) tables of the resident points (ScoreParams), nullptr when xs are ad hoc
 };
 
-constexpr int SLOT_DOUBLES_PER_WARP = CLOSYR_REG_SLOTS * POINTS_PER_LANE * 32;
+constexpr int SLOT_DOUBLES_PER_WARP = CLOSYR_REG_SLOTS * POINTS_PER_LANE * 32;   // 4 KiB
+constexpr int LIST_DOUBLES_PER_WARP = CHUNK_POINTS;                              // 1 KiB: the reported points of one chunk
 
-// shared memory of a CTA: [warp slots | constants | `nlvl` doubles of scratch | threaded code (ncode + 1 entries) |
-// the program as the caller wrote it (ncode words)]
+// shared memory of a CTA: [warp slots | warp lists | `nlvl` chunk sums | threaded code (ncode + 1 entries: the dispatch
+// loop prefetches one entry past END)]
 struct SmemLayout {
-    double *sconst, *slvl;
+    double *list, *slvl;
     TInsn *tcode;
-    uint32_t *raw;
 };
-__device__ __forceinline__ SmemLayout smem_layout(unsigned char *smem, int nthreads, uint32_t nk, int nlvl, uint32_t ncode)
+__device__ __forceinline__ SmemLayout smem_layout(unsigned char *smem, int nwarps, int nlvl)
 {
     SmemLayout L;
-    L.sconst = reinterpret_cast<double *>(smem) + (nthreads >> 5) * SLOT_DOUBLES_PER_WARP;
-    L.slvl = L.sconst + ((nk + 1) & ~1u);
+    L.list = reinterpret_cast<double *>(smem) + nwarps * SLOT_DOUBLES_PER_WARP;
+    L.slvl = L.list + nwarps * LIST_DOUBLES_PER_WARP;
     L.tcode = reinterpret_cast<TInsn *>(L.slvl + ((nlvl + 1) & ~1));      // 16-byte aligned
-    L.raw = reinterpret_cast<uint32_t *>(L.tcode + ncode + 1);
     return L;
 }
 
-// translates the staged program into threaded code (one entry per word, one word per thread and pass) and collects
-// the program's properties; every thread of the CTA calls it after the program and its constants are visible
-__device__ __forceinline__ Staged finish_stage(const SmemLayout &L, uint32_t ncode, unsigned char *smem, int tid, int nthreads,
-                                               const double *leaf_tab, int64_t leaf_stride, uint32_t *s_pflags)
+// Translates every program of a shard into threaded code once per upload (the layout the interpreters dispatch on:
+// vm.cuh decode_insn) and writes one descriptor per expression.  One warp per expression.
+__global__ void __launch_bounds__(256) prepare_kernel(const PrepareParams p)
 {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= p.pop.n_expr) return;
+    const uint32_t c0 = p.pop.code_off[e], c1 = p.pop.code_off[e + 1];
+    const uint32_t k0 = p.pop.const_off[e], k1 = p.pop.const_off[e + 1];
+    const uint32_t ncode = c1 - c0;
+    const uint32_t *gc = p.pop.code + (c0 - p.pop.code_base);
+    const double *gk = p.pop.consts + (k0 - p.pop.const_base);
+    TInsn *out = reinterpret_cast<TInsn *>(p.tcode) + (c0 - p.pop.code_base);
     uint32_t pf = 0;
-    for (uint32_t i = tid; i <= ncode; i += nthreads) {      // entry `ncode` is the slack the prefetch reads
+    for (uint32_t i = lane; i < ncode; i += 32) {
         TInsn t;
-        pf |= decode_insn(i < ncode ? L.raw[i] : 0u, L.sconst, leaf_tab != nullptr, leaf_stride, t);
-        L.tcode[i] = t;
+        pf |= decode_insn(gc[i], gk, k1 - k0, p.have_tab != 0, p.leaf_stride, t);
+        out[i] = t;
     }
-    if (pf) atomicOr(s_pflags, pf);
-    __syncthreads();
-    Staged st;
-    st.sconst = L.sconst;
-    st.slvl = L.slvl;
-    st.tcode_addr = (uint32_t)__cvta_generic_to_shared(L.tcode);
-    st.slot_addr = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<double *>(smem) + (tid >> 5) * SLOT_DOUBLES_PER_WARP + (tid & 31));
-    st.pflags = *s_pflags;
-    st.leaf_tab = leaf_tab;
-    return st;
+    pf = __reduce_or_sync(FULL, pf);
+    if (lane == 0) {
+        ExprDesc d;
+        d.tc_off = c0 - p.pop.code_base;
+        d.ncode_pf = ncode | (pf << 16);
+        d.meta = p.pop.meta[e];
+        d.k_off = k0 - p.pop.const_base;
+        p.desc[e] = d;
+    }
 }
 
-// copies one program into shared memory with plain loads (eval_kernel: one warp per expression)
-__device__ __forceinline__ Staged stage_program(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
-                                                int nthreads, int nlvl, uint32_t *s_pflags)
+// The slow half of a chunk, for the warp that owns it: some of its points were reported by the fast pass (or the chunk has
+// no fast pass at all).  The reported points are compacted inside the warp and re-evaluated with the complete algebra,
+// 64 points (2 per lane) per pass; then the chunk's residuals again from the merged values.  No other warp is involved:
+// a CTA's warps take chunks from a shared counter, so a warp that is busy here simply takes fewer chunks.
+// ev = this lane's points that need the complete algebra, v = the fast pass' values of the others.
+// `mode` (shared, may be nullptr) is the CTA's hint "chunks around here leave the real line almost everywhere": while
+// it is set the fast pass is skipped.  Both evaluators give bit-identical values wherever the fast path is valid, so
+// the hint cannot change a score.
+// A function of its own: the common path of the kernel keeps none of this state in registers.
+constexpr int CPLX_POINTS = 2;       // points per lane of the complete-algebra interpreter
+struct WarpSlowResult { double v[4]; double mx; uint32_t nr, used; };
+
+__device__ __noinline__ WarpSlowResult warp_slow(const double *__restrict__ sconst, const uint32_t tcode_addr,
+                                                 const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
+                                                 double *__restrict__ list, uint32_t *mode, const bool ran_fast,
+                                                 const double *__restrict__ xs, const double *__restrict__ ys,
+                                                 const int64_t base, const uint32_t valid, const uint32_t ev_in,
+                                                 const uint32_t quirk_off_plus1, const uint32_t sum_addr,
+                                                 const double v0, const double v1, const double v2, const double v3)
 {
-    const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
-    const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
-    const uint32_t ncode = c1 - c0, nk = k1 - k0;
-    const SmemLayout L = smem_layout(smem, nthreads, nk, nlvl, ncode);
-    const double *gk = pop.consts + (k0 - pop.const_base);
-    const uint32_t *gc = pop.code + (c0 - pop.code_base);
-    for (uint32_t i = tid; i < nk; i += nthreads) L.sconst[i] = gk[i];
-    for (uint32_t i = tid; i < ncode; i += nthreads) L.raw[i] = gc[i];
-    if (tid == 0) *s_pflags = 0;
-    __syncthreads();
-    return finish_stage(L, ncode, smem, tid, nthreads, nullptr, 0, s_pflags);
+    const int lane = threadIdx.x & 31;
+    WarpSlowResult out;
+    uint32_t ev = ev_in;
+    double v[4] = { v0, v1, v2, v3 };
+    if (quirk_off_plus1) {
+        // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
+        ev = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? sconst[quirk_off_plus1 - 1 + base + j] : 0.0;
+    }
+    // warp-wide compaction of the reported points
+    const uint32_t mine = __popc(ev);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint32_t pos = incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
+    __syncwarp();
+    uint32_t left_real = 0;
+    constexpr uint32_t TASK = 32 * CPLX_POINTS;
+    for (uint32_t t0 = 0; t0 < total; t0 += TASK) {
+        CplxArgs<CPLX_POINTS> ca;
+#pragma unroll
+        for (int j = 0; j < CPLX_POINTS; j++) {
+            const uint32_t r = t0 + j * 32 + lane;
+            ca.idx[j] = __double_as_longlong(list[r < total ? r : t0]);          // idle lanes repeat the task's first point
+        }
+        const CplxResult<CPLX_POINTS> cr = deep ? run_cplx<CPLX_POINTS, true>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab)
+                                                : run_cplx<CPLX_POINTS, false>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
+        left_real |= cr.left_real;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < CPLX_POINTS; j++) {
+            const uint32_t r = t0 + j * 32 + lane;
+            if (r < total) list[r] = ((cr.nonreal >> j) & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : cr.out[j];   // NaN marks "not a real number"
+        }
+    }
+    __syncwarp();
+    pos = incl - mine;
+    out.nr = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if ((ev >> j) & 1u) {
+            const double r = list[pos++];
+            if (r != r) { v[j] = __longlong_as_double(0x7ff0000000000000ll); out.nr |= 1u << j; }
+            else v[j] = r;
+        }
+    }
+    __syncwarp();                                   // the list is reused by the warp's next chunk
+    out.used = total != 0 ? 1u : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) out.v[j] = v[j];
+    out.mx = chunk_residuals(v, ys + base, valid, sum_addr);
+    if (mode && lane == 0) {
+        if (ran_fast) { if (total * 4u >= (uint32_t)CHUNK_POINTS * 3u) *(volatile uint32_t *)mode = 1u; }     // >= 75 % of the chunk
+        else if (!left_real) *(volatile uint32_t *)mode = 0u;
+    }
+    return out;
+}
+
+// ---- TMA bulk copy (cp.async.bulk + mbarrier): the threaded code of a program is 16-byte aligned and a whole number
+// of 16-byte entries
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// largest of a warp's non-negative doubles: their bit patterns order like their values
+__device__ __forceinline__ double warp_max_nonneg(double m)
+{
+    const uint32_t hi = (uint32_t)__double2hiint(m);
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? (uint32_t)__double2loint(m) : 0u);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 // One round of a CTA = one 128-point chunk per warp: v[j] = f(x[j]) for the lane's 4 points (+Inf where the value is
@@ -131,7 +245,6 @@ struct Round {
     double *list;          // [warps * 128] indices of the reported points, replaced in place by their results
     uint32_t *counts;      // [2][32] reported points per warp, double-buffered by round parity
 };
-constexpr int CPLX_POINTS = 2;       // points per lane of the complete-algebra interpreter
 
 struct CplxPassResult { double v[4]; uint32_t nr, mode; };
 
@@ -234,77 +347,83 @@ __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sc
     return out;
 }
 
-// ---- TMA bulk copies (cp.async.bulk + mbarrier): the population buffer is laid out for it (every program and
-// every constant pool starts on a 16-byte boundary and is a multiple of 16 bytes long)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
-// largest of a warp's non-negative doubles: their bit patterns order like their values
-__device__ __forceinline__ double warp_max_nonneg(double m)
+// stages the threaded code of a program with one TMA bulk copy; every thread of the CTA calls it, thread 0 issues the
+// copy and everybody waits on the mbarrier (single use: parity 0)
+__device__ __forceinline__ void stage_tcode_tma(TInsn *dst, const uint4 *src, uint32_t ncode, unsigned long long *bar, int tid)
 {
-    const uint32_t hi = (uint32_t)__double2hiint(m);
-    const uint32_t mh = __reduce_max_sync(FULL, hi);
-    const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? (uint32_t)__double2loint(m) : 0u);
-    return __hiloint2double((int)mh, (int)ml);
-}
-
-// stages one program with two TMA bulk copies and translates it; every thread of the CTA calls it, thread 0 issues
-// the copies and everybody waits on the mbarrier (single use: parity 0)
-__device__ __forceinline__ Staged stage_program_tma(const DevPopulation &pop, int64_t e, unsigned char *smem, int tid,
-                                                    int nthreads, int nlvl, unsigned long long *bar, const double *leaf_tab,
-                                                    int64_t leaf_stride, uint32_t *s_pflags)
-{
-    const uint32_t c0 = pop.code_off[e], c1 = pop.code_off[e + 1];
-    const uint32_t k0 = pop.const_off[e], k1 = pop.const_off[e + 1];
-    const uint32_t ncode = c1 - c0, nk = k1 - k0;
-    const SmemLayout L = smem_layout(smem, nthreads, nk, nlvl, ncode);
     if (tid == 0) {
-        *s_pflags = 0;
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar, ncode * 4u + nk * 8u);
-        if (nk) bulk_g2s(L.sconst, pop.consts + (k0 - pop.const_base), nk * 8u, bar);
-        bulk_g2s(L.raw, pop.code + (c0 - pop.code_base), ncode * 4u, bar);
+        mbar_expect_tx(bar, ncode * 16u);
+        bulk_g2s(dst, src, ncode * 16u, bar);
     }
     __syncthreads();                 // the initialised barrier is visible to every waiter
     mbar_wait(bar, 0);
-    return finish_stage(L, ncode, smem, tid, nthreads, leaf_tab, leaf_stride, s_pflags);
 }
 
-__global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
+// what both scoring kernels write for a finished (expression, tile)
+__device__ __forceinline__ void emit_tile(const ScoreParams &p, int64_t e, int tile, int leafs, bool const_throws,
+                                          double tile_sum, double tile_max, uint32_t tile_nonreal, bool tile_full)
+{
+    if (p.final_scores) {
+        uint8_t rf = tile_full ? CL_R_FULL_SEMANTICS : 0;
+        double score;
+        if (const_throws) {                                            // eval.clj:83-96 throws => min-score
+            score = CLOSYR_MIN_SCORE;
+            rf |= CL_R_MIN_SCORE;
+        } else score = score_formula(tile_sum, tile_max, p.n, leafs);
+        p.scores[e] = score;
+        p.rflags[e] = rf;
+    } else {
+        double *out = p.partials + ((p.partial_tile_offset + tile) * p.pop.n_expr + e) * 3;
+        out[0] = tile_sum;
+        out[1] = tile_max;
+        out[2] = (double)tile_nonreal + (tile_full ? 0.25 : 0.0);     // fraction carries the diagnostic bit
+    }
+}
+
+// index-aligned pairwise tree over the chunk sums (a missing right child leaves the left one unchanged); one warp
+__device__ __forceinline__ void tree_reduce_chunks(double *slvl, int cnt, int lane)
+{
+    for (int stride = 1; stride < cnt; stride <<= 1) {
+        for (int i = lane * 2 * stride; i + stride < cnt; i += 64 * stride) slvl[i] = slvl[i] + slvl[i + stride];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scoring is two kernels.
+//
+// score_fast_kernel: one small CTA per (expression, tile of points), several CTAs per SM.  The program's threaded code
+// arrives with ONE TMA bulk copy; after that the warps are on their own: each takes the tile's 128-point chunks from a
+// shared counter and runs the IEEE-real fast pass on them.  The only CTA barriers are the one before the first chunk and
+// the one before the reduction, and one CTA's staging and reduction overlap the other CTAs' arithmetic.  The fast
+// interpreter is compact enough for the SM's instruction cache to hold what warps of DIFFERENT programs execute.  A
+// chunk in which some point was reported (it left the real line, or met an infinity) is only marked; a tile with marked
+// chunks leaves its chunk sums in global memory and queues itself for the second kernel.
+//
+// score_slow_kernel: one CTA of 32 warps per queued tile, ONE program per SM, the warps move through the rounds in
+// step (fast pass again on the marked chunks, CTA-wide compaction of the reported points, complete algebra).  The
+// complete-algebra interpreter and the complex functions behind it are ~150 KB of code: warps that sit in different
+// places of it (different programs on one SM, or one program without the round structure) spend most of their time
+// waiting for instructions (measured: 47 stalled warp-cycles per issued instruction on `no_instruction`).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t WL_ALL_CHUNKS = 0x80000000u;      // work-list entry: the fast kernel evaluated nothing of this tile
+
+__global__ void __launch_bounds__(FAST_MAX_WARPS * 32, FAST_MIN_CTAS) score_fast_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_max[MAX_SCORE_WARPS];
-    __shared__ uint32_t s_nonreal[MAX_SCORE_WARPS], s_full[MAX_SCORE_WARPS];
+    __shared__ double s_max[FAST_MAX_WARPS];
+    __shared__ uint32_t s_marked[FAST_MAX_WARPS];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t item = blockIdx.x;
     const int64_t e = item / p.n_tiles;
     const int tile = (int)(item - e * p.n_tiles);
-    const uint32_t meta = p.pop.meta[e];
+    const uint4 dq = __ldg(reinterpret_cast<const uint4 *>(p.pop.desc + e));
+    const uint32_t ncode = dq.y & 0xffffu, pflags = dq.y >> 16, meta = dq.z;
     const int leafs = (int)(meta & 0xffffu);
     const uint32_t flags = (meta >> 16) & 0xffu;
 
@@ -322,48 +441,142 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         }
         return;
     }
+    if ((flags & CL_F_CONST) || (pflags & PF_NO_FAST)) {
+        // constant expressions and programs the IEEE path cannot express: everything is the second kernel's
+        if (tid == 0) p.worklist[atomicAdd(p.wl_count, 1u)] = (uint32_t)item | WL_ALL_CHUNKS;
+        return;
+    }
 
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_pflags;
-    const Staged st = stage_program_tma(p.pop, e, smem, tid, blockDim.x, p.chunks_per_tile + (blockDim.x >> 5) * CHUNK_POINTS,
-                                        &s_bar, p.leaf_tab, p.leaf_stride, &s_pflags);
-    const bool is_const = (flags & CL_F_CONST) != 0;
-    const uint32_t aux = p.pop.aux[e];
-    const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
-    const uint32_t quirk_off = aux & 0xffffu;
+    // shared memory: [warp slots | chunk sums | threaded code]
+    double *const slvl = reinterpret_cast<double *>(smem) + nwarps * SLOT_DOUBLES_PER_WARP;
+    TInsn *const tcode = reinterpret_cast<TInsn *>(slvl + ((p.chunks_per_tile + 1) & ~1));
+    if (tid == 0) s_next = 0;
+    stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);
 
+    const uint32_t tcode_addr = smem_u32(tcode);
+    const uint32_t slot_addr = smem_u32(reinterpret_cast<double *>(smem) + warp * SLOT_DOUBLES_PER_WARP + lane);
     const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
     int64_t c_hi = c_lo + p.chunks_per_tile;
     if (c_hi > p.chunk_end) c_hi = p.chunk_end;
     const int cnt = (int)(c_hi - c_lo);
+    const uint32_t slvl_addr = smem_u32(slvl);
+    double warp_mx = 0.0;
+    uint32_t marked = 0;
+    for (;;) {
+        int ci = 0;
+        if (lane == 0) ci = (int)atomicAdd(&s_next, 1u);
+        ci = __shfl_sync(FULL, ci, 0);
+        if (ci >= cnt) break;
+        const int64_t base = (c_lo + ci) * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        // xs, ys and every table row are padded to whole chunks (x = 1.0, y = 0.0), so a lane always loads its 4 points
+        const int64_t left = p.n - base;
+        const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
+        const uint32_t sum_addr = slvl_addr + (uint32_t)ci * 8u;
+        const RealResult<4> rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+        if (__any_sync(FULL, rr.ev != 0)) {
+            marked = 1;
+            if (lane == 0) sts_f64(sum_addr, __longlong_as_double(0x7ff8000000000000ll));     // a sum of residuals is never NaN
+        } else warp_mx = max_nonneg(warp_mx, rr.mx);
+    }
+    warp_mx = warp_max_nonneg(warp_mx);
+    if (lane == 0) { s_max[warp] = warp_mx; s_marked[warp] = marked; }
+    __syncthreads();
+    if (warp != 0) return;
+    const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
+    const uint32_t tile_marked = __reduce_or_sync(FULL, lane < nwarps ? s_marked[lane] : 0u);
+    if (tile_marked) {
+        double *out = p.csum + item * p.chunks_per_tile;
+        for (int i = lane; i < cnt; i += 32) out[i] = slvl[i];
+        if (lane == 0) {
+            p.cmax[item] = tile_max;
+            __threadfence();
+            p.worklist[atomicAdd(p.wl_count, 1u)] = (uint32_t)item;
+        }
+        return;
+    }
+    tree_reduce_chunks(slvl, cnt, lane);
+    if (lane == 0) emit_tile(p, e, tile, leafs, false, cnt > 0 ? slvl[0] : 0.0, tile_max, 0u, false);
+}
 
+__global__ void __launch_bounds__(SLOW_WARPS * 32, 1) score_slow_kernel(const ScoreParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double s_max[SLOW_WARPS];
+    __shared__ uint32_t s_nonreal[SLOW_WARPS], s_full[SLOW_WARPS];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_counts[64];
-    double *const list = st.slvl + p.chunks_per_tile;
-    const uint32_t slvl_addr = smem_u32(st.slvl);
-    const bool fast_ok = !is_const && !(st.pflags & PF_NO_FAST);
+    __shared__ int s_nmarked;
+    if (blockIdx.x >= *p.wl_count) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t wl = p.worklist[blockIdx.x];
+    const bool all_chunks = (wl & WL_ALL_CHUNKS) != 0;
+    const int64_t item = wl & ~WL_ALL_CHUNKS;
+    const int64_t e = item / p.n_tiles;
+    const int tile = (int)(item - e * p.n_tiles);
+    const uint4 dq = __ldg(reinterpret_cast<const uint4 *>(p.pop.desc + e));
+    const uint32_t ncode = dq.y & 0xffffu, pflags = dq.y >> 16, meta = dq.z;
+    const int leafs = (int)(meta & 0xffffu);
+    const uint32_t flags = (meta >> 16) & 0xffu;
+
+    // shared memory: [warp slots | compaction list | chunk sums | marked chunks (u16) | threaded code]
+    double *const list = reinterpret_cast<double *>(smem) + nwarps * SLOT_DOUBLES_PER_WARP;
+    double *const slvl = list + nwarps * CHUNK_POINTS;
+    uint16_t *const chunks = reinterpret_cast<uint16_t *>(slvl + ((p.chunks_per_tile + 2) & ~1));
+    TInsn *const tcode = reinterpret_cast<TInsn *>(reinterpret_cast<unsigned char *>(chunks) + ((p.chunks_per_tile * 2 + 15) & ~15));
+    const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
+    int64_t c_hi = c_lo + p.chunks_per_tile;
+    if (c_hi > p.chunk_end) c_hi = p.chunk_end;
+    const int cnt = (int)(c_hi - c_lo);
+    // the fast kernel's chunk sums; NaN marks the chunks it left to this kernel
+    if (!all_chunks) {
+        const double *in = p.csum + item * p.chunks_per_tile;
+        for (int i = tid; i < cnt; i += blockDim.x) slvl[i] = in[i];
+    }
+    stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);       // contains the barrier after the loads above
+    if (warp == 0) {
+        int n = 0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int c = c0 + lane;
+            const bool m = c < cnt && (all_chunks || slvl[c] != slvl[c]);
+            const uint32_t mask = __ballot_sync(FULL, m);
+            if (m) chunks[n + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)c;
+            n += __popc(mask);
+        }
+        if (lane == 0) s_nmarked = n;
+    }
+    __syncthreads();
+    const int nmarked = s_nmarked;
+
+    const double *const sconst = p.pop.consts + dq.w;
+    const uint32_t tcode_addr = smem_u32(tcode);
+    const uint32_t slot_addr = smem_u32(reinterpret_cast<double *>(smem) + warp * SLOT_DOUBLES_PER_WARP + lane);
+    const bool is_const = (flags & CL_F_CONST) != 0;
+    uint32_t quirk_off_plus1 = 0;
+    if (is_const) {
+        const uint32_t aux = p.pop.aux[e];
+        if ((aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n) quirk_off_plus1 = (aux & 0xffffu) + 1u;
+    }
+    const uint32_t slvl_addr = smem_u32(slvl);
+    const bool fast_ok = !is_const && !(pflags & PF_NO_FAST);
     double warp_mx = 0.0;
     uint32_t nonreal = 0, mode = 0, parity = 0, used_full = 0;
-    for (int64_t c0 = c_lo; c0 < c_hi; c0 += nwarps, parity ^= 1u) {
-        const int64_t c = c0 + warp;
-        const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        // xs, ys and every table row are padded to whole chunks (x = 1.0, y = 0.0), so a lane always loads its 4 points
-        const int64_t left = c < c_hi ? p.n - base : 0;
+    for (int r0 = 0; r0 < nmarked; r0 += nwarps, parity ^= 1u) {
+        const bool have = r0 + warp < nmarked;
+        const int ci = have ? (int)chunks[r0 + warp] : 0;
+        const int64_t base = (c_lo + ci) * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        const int64_t left = have ? p.n - base : 0;
         const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
-        const uint32_t sum_addr = slvl_addr + (uint32_t)(c - c_lo) * 8u;
+        // an idle warp's sum goes to the scratch word behind the chunk sums
+        const uint32_t sum_addr = slvl_addr + (uint32_t)(have ? ci : p.chunks_per_tile) * 8u;
         const bool fast = fast_ok && mode == 0;
         RealResult<4> rr;
         rr.ev = valid;
         rr.mx = 0.0;
         rr.v[0] = rr.v[1] = rr.v[2] = rr.v[3] = 0.0;
-        if (fast && c < c_hi)
-            rr = run_real<4>(st.tcode_addr, st.slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
-        // nothing reported anywhere in the CTA (the common round): one barrier, the fast pass has done everything
-        if (fast && !__syncthreads_or(rr.ev != 0)) {
-            warp_mx = max_nonneg(warp_mx, rr.mx);
-            continue;
-        }
-        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, p.leaf_tab, (st.pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
-                                              base, valid, rr.ev, quirk ? quirk_off + 1u : 0u, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
+        if (fast && have)
+            rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+        const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
+                                              base, valid, rr.ev, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
         nonreal += __popc(rs.nr);
         used_full |= rs.used;
@@ -374,33 +587,13 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     if (lane == 0) { s_max[warp] = warp_mx; s_nonreal[warp] = nonreal; s_full[warp] = used_full; }
     __syncthreads();
     if (warp != 0) return;
-
-    // index-aligned pairwise tree over the chunk sums (a missing right child leaves the left one unchanged)
-    for (int stride = 1; stride < cnt; stride <<= 1) {
-        for (int i = lane * 2 * stride; i + stride < cnt; i += 64 * stride) st.slvl[i] = st.slvl[i] + st.slvl[i + stride];
-        __syncwarp();
-    }
-    // max, counts and flags of the warps: one lane per warp, then shuffles (all three are order-independent)
-    const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
+    tree_reduce_chunks(slvl, cnt, lane);
+    double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
     const uint32_t tile_nonreal = __reduce_add_sync(FULL, lane < nwarps ? s_nonreal[lane] : 0u);
     const uint32_t tile_full = __reduce_or_sync(FULL, lane < nwarps ? s_full[lane] : 0u);
     if (lane != 0) return;
-    const double tile_sum = cnt > 0 ? st.slvl[0] : 0.0;
-    if (p.final_scores) {
-        uint8_t rf = tile_full ? CL_R_FULL_SEMANTICS : 0;
-        double score;
-        if (is_const && !quirk && tile_nonreal != 0) {                 // eval.clj:83-96 throws => min-score
-            score = CLOSYR_MIN_SCORE;
-            rf |= CL_R_MIN_SCORE;
-        } else score = score_formula(tile_sum, tile_max, p.n, leafs);
-        p.scores[e] = score;
-        p.rflags[e] = rf;
-    } else {
-        double *out = p.partials + ((p.partial_tile_offset + tile) * p.pop.n_expr + e) * 3;
-        out[0] = tile_sum;
-        out[1] = tile_max;
-        out[2] = (double)tile_nonreal + (tile_full ? 0.25 : 0.0);     // fraction carries the diagnostic bit
-    }
+    if (!all_chunks) tile_max = max_nonneg(tile_max, p.cmax[item]);
+    emit_tile(p, e, tile, leafs, is_const && !quirk_off_plus1 && tile_nonreal != 0, cnt > 0 ? slvl[0] : 0.0, tile_max, tile_nonreal, tile_full != 0);
 }
 
 // combines per-tile partials in global tile order with the same aligned binary tree, then the epilogue
@@ -458,38 +651,43 @@ __global__ void __launch_bounds__(32) eval_kernel(const EvalParams p)
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x;
     const int64_t e = blockIdx.x;
-    const uint32_t meta = p.pop.meta[e];
+    const uint4 dq = __ldg(reinterpret_cast<const uint4 *>(p.pop.desc + e));
+    const uint32_t ncode = dq.y & 0xffffu, pflags = dq.y >> 16, meta = dq.z;
     const uint32_t flags = (meta >> 16) & 0xffu;
     if (flags & (CL_F_UNSUPPORTED | CL_F_NIL)) {
         if (lane == 0) p.status[e] = 1;
         return;
     }
-    __shared__ uint32_t s_pflags;
-    const Staged st = stage_program(p.pop, e, smem, lane, 32, CHUNK_POINTS, &s_pflags);
+    const SmemLayout L = smem_layout(smem, 1, 2);
+    for (uint32_t i = lane; i < ncode; i += 32) reinterpret_cast<uint4 *>(L.tcode)[i] = __ldg(p.pop.tcode + dq.x + i);
+    __syncwarp();
+    const double *const sconst = p.pop.consts + dq.w;
+    const uint32_t tcode_addr = smem_u32(L.tcode);
+    const uint32_t slot_addr = smem_u32(reinterpret_cast<double *>(smem) + lane);
     const bool is_const = (flags & CL_F_CONST) != 0;
-    const uint32_t aux = p.pop.aux[e];
-    const bool quirk = is_const && (aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n;
-    const uint32_t quirk_off = aux & 0xffffu;
+    uint32_t quirk_off_plus1 = 0;
+    if (is_const) {
+        const uint32_t aux = p.pop.aux[e];
+        if ((aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n) quirk_off_plus1 = (aux & 0xffffu) + 1u;
+    }
     const int64_t nchunks = (p.n + CHUNK_POINTS - 1) / CHUNK_POINTS;
-    __shared__ uint32_t s_counts[64];
-    __shared__ double s_sum;                                   // the chunk sums are not used here
     uint32_t nonreal = 0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int64_t c = 0; c < nchunks; c++) {
         const int64_t base = c * CHUNK_POINTS + lane * POINTS_PER_LANE;
         const int64_t left = p.n - base;
         const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
-        // every point through the complete algebra (one warp per expression: there is no load to balance, and the
-        // report path evaluates few points); xs doubles as the y vector of the unused residuals
-        const RoundSlowResult rs = round_slow(st.sconst, st.tcode_addr, st.slot_addr, nullptr, (st.pflags & PF_DEEP) != 0, st.slvl, s_counts + (c & 1) * 32, p.xs, p.xs,
-                                              base, valid, valid, quirk ? quirk_off + 1u : 0u, smem_u32(&s_sum), 0.0, 0.0, 0.0, 0.0);
+        // every point through the complete algebra (the values are wanted, not the residuals: xs doubles as the y vector
+        // and the chunk sum goes to a scratch word)
+        const WarpSlowResult rs = warp_slow(sconst, tcode_addr, slot_addr, nullptr, (pflags & PF_DEEP) != 0, L.list, nullptr, false, p.xs, p.xs,
+                                            base, valid, valid, quirk_off_plus1, smem_u32(L.slvl), 0.0, 0.0, 0.0, 0.0);
         nonreal += __popc(rs.nr);
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if ((valid >> j) & 1u) p.out_f[e * p.n + base + j] = ((rs.nr >> j) & 1u) ? inf : rs.v[j];
     }
     nonreal = __reduce_add_sync(FULL, nonreal);
-    if (lane == 0) p.status[e] = (is_const && !quirk && nonreal != 0) ? 2 : 0;
+    if (lane == 0) p.status[e] = (is_const && !quirk_off_plus1 && nonreal != 0) ? 2 : 0;
 }
 
 // compute-score-from-actuals-and-expecteds (ops.clj:98-116) on given f values: one warp, same reduction tree
@@ -573,8 +771,6 @@ __global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restric
 
 }  // namespace
 
-int score_warps(int32_t chunks_per_tile);
-
 void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab, void *stream)
 {
     if (stride <= 0) return;
@@ -583,15 +779,28 @@ void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab,
     leaf_table_kernel<<<(unsigned)((quads + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(xs, n, stride, tab);
 }
 
-void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream)
+void launch_prepare(const PrepareParams &p, void *stream)
+{
+    if (p.pop.n_expr <= 0) return;
+    const int threads = 256, per_block = threads / 32;
+    prepare_kernel<<<(unsigned)((p.pop.n_expr + per_block - 1) / per_block), threads, 0, (cudaStream_t)stream>>>(p);
+}
+
+int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream)
 {
     const int64_t items = p.pop.n_expr * p.n_tiles;
-    if (items <= 0) return;
-    const int warps = score_warps(p.chunks_per_tile);
+    if (items <= 0) return 0;
     // opt in to > 48 KiB of dynamic shared memory; the attribute is per device, so it is set at every launch
-    if (smem_bytes > 48 * 1024)
-        cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    score_kernel<<<(unsigned)items, warps * 32, smem_bytes, (cudaStream_t)stream>>>(p);
+    const size_t smem_fast = (size_t)p.warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)((p.chunks_per_tile + 1) & ~1) * 8 +
+                             ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
+    const size_t smem_slow = (size_t)SLOW_WARPS * (SLOT_DOUBLES_PER_WARP + CHUNK_POINTS) * 8 + (size_t)((p.chunks_per_tile + 2) & ~1) * 8 +
+                             (size_t)((p.chunks_per_tile * 2 + 15) & ~15) + ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
+    if (smem_fast > 48 * 1024) cudaFuncSetAttribute(score_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+    cudaFuncSetAttribute(score_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slow);
+    cudaMemsetAsync(p.wl_count, 0, sizeof(uint32_t), (cudaStream_t)stream);
+    score_fast_kernel<<<(unsigned)items, p.warps * 32, smem_fast, (cudaStream_t)stream>>>(p);
+    score_slow_kernel<<<(unsigned)items, SLOW_WARPS * 32, smem_slow, (cudaStream_t)stream>>>(p);
+    return 2;
 }
 
 void launch_finalize(const FinalizeParams &p, void *stream)
@@ -617,20 +826,18 @@ void launch_fp64_probe(double *out, int iters, int blocks, void *stream)
     fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters);
 }
 
-size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps)
+size_t eval_smem_bytes(uint32_t max_code_words)
 {
-    // [warp slots | constants | chunk sums + the compaction list | threaded code | the program]  (smem_layout)
-    return (size_t)warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)((max_consts + 1) & ~1u) * 8 +
-           (size_t)((chunks_per_tile + warps * CHUNK_POINTS + 1) & ~1) * 8 +
-           ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + (size_t)max_code_words * 4 + 16;
+    // [warp slots | warp list | 2 scratch doubles | threaded code + the entry the dispatch loop prefetches past END]  (smem_layout)
+    return (size_t)(SLOT_DOUBLES_PER_WARP + LIST_DOUBLES_PER_WARP) * 8 + 16 + ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
 }
 int score_warps(int32_t chunks_per_tile)
 {
-    // CLOSYR_SCORE_WARPS (a power of two <= 32) caps the CTA size: a tuning knob for measurements, not an API
+    // CLOSYR_SCORE_WARPS (a power of two <= 16) sets the CTA size: a tuning knob for measurements, not an API
     static const int cap = [] {
         const char *e = getenv("CLOSYR_SCORE_WARPS");
         const int v = e ? atoi(e) : 0;
-        return (v >= 1 && v <= MAX_SCORE_WARPS && (v & (v - 1)) == 0) ? v : MAX_SCORE_WARPS;
+        return (v >= 1 && v <= FAST_MAX_WARPS && (v & (v - 1)) == 0) ? v : 8;
     }();
     int w = 1;
     while (w < cap && w < chunks_per_tile) w <<= 1;

@@ -19,7 +19,28 @@ struct DevPopulation {                // device pointers of one resident shard
     uint32_t code_base;               // code_off value of the shard's first expression
     uint32_t const_base;
     int64_t n_expr;
+    // what prepare_kernel leaves per shard (ctx.cu launches it once per upload / set_points): the threaded code of every
+    // program (vm.cuh TInsn, 16 bytes per ISA word, same word index relative to the shard) and one descriptor per expression
+    const uint4 *tcode;
+    const struct ExprDesc *desc;
 };
+
+// one 16-byte load tells a CTA everything about its expression
+struct __align__(16) ExprDesc {
+    uint32_t tc_off;                  // first threaded-code entry of the program (index into DevPopulation::tcode)
+    uint32_t ncode_pf;                // number of entries (low 16 bits) | PF_* program properties << 16
+    uint32_t meta;                    // CLOSYR_META word
+    uint32_t k_off;                   // first constant of the program (index into DevPopulation::consts)
+};
+
+struct PrepareParams {
+    DevPopulation pop;                // tcode / desc are the outputs
+    uint4 *tcode;
+    ExprDesc *desc;
+    int32_t have_tab;                 // leaf tables exist: SRCX functions become table loads
+    int64_t leaf_stride;
+};
+void launch_prepare(const PrepareParams &p, void *stream);
 
 struct ScoreParams {
     DevPopulation pop;
@@ -27,7 +48,8 @@ struct ScoreParams {
     const double *ys;
     int64_t n;                        // total number of points of the run
     int64_t chunk_begin, chunk_end;   // 128-point chunks [begin, end) evaluated by this launch
-    int32_t chunks_per_tile;          // power of two; one warp reduces one tile
+    int32_t chunks_per_tile;          // power of two; one CTA reduces one tile
+    int32_t warps;                    // warps per CTA (score_warps)
     int32_t n_tiles;                  // tiles per expression in this launch
     int32_t max_leafs;
     int32_t final_scores;             // 1: one tile covers every point -> write scores; 0: write partials
@@ -40,6 +62,11 @@ struct ScoreParams {
     // `leaf_stride` doubles; nullptr = compute in the kernel
     const double *leaf_tab;
     int64_t leaf_stride;
+    // hand-over from score_fast_kernel to score_slow_kernel (device scratch owned by the context)
+    double *csum;                     // [items][chunks_per_tile] chunk sums of the queued tiles, NaN = chunk left to the slow kernel
+    double *cmax;                     // [items] largest residual of the chunks the fast kernel finished
+    uint32_t *worklist;               // [items] queued (expression, tile) items
+    uint32_t *wl_count;               // number of queued items (zeroed by launch_score)
 };
 
 constexpr int LEAF_TAB_ROWS = CL_ACOS - CL_RECIP + 1;
@@ -67,12 +94,12 @@ struct EvalParams {
     uint8_t *status;                  // [n_expr]
 };
 
-void launch_score(const ScoreParams &p, size_t smem_bytes, void *stream);
+int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream);     // returns the number of kernels launched
 void launch_finalize(const FinalizeParams &p, void *stream);
 void launch_eval(const EvalParams &p, size_t smem_bytes, void *stream);
 void launch_score_values(const double *f, const double *ys, int64_t n, int32_t leafs, double *out3, void *stream);
 void launch_fp64_probe(double *out, int iters, int blocks, void *stream);
-size_t score_smem_bytes(uint32_t max_code_words, uint32_t max_consts, int32_t chunks_per_tile, int warps);
+size_t eval_smem_bytes(uint32_t max_code_words);
 int score_warps(int32_t chunks_per_tile);
 constexpr int MAX_CHUNKS_PER_TILE = 1024;   // per-chunk sums of a tile live in shared memory (8 KiB)
 

@@ -458,10 +458,12 @@ __constant__ uint8_t closyr_th_of_function[CL_ABS - CL_NEG + 1] = {
 constexpr uint32_t VM_TAB_MASK = 0x1FCDu;
 
 // one ISA word -> one threaded-code entry; returns the PF_* bits the instruction implies
-__device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__restrict__ sconst, bool have_tab,
+// (sconst = the program's constant pool of nk doubles; an index beyond it reads as NaN)
+__device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__restrict__ sconst, uint32_t nk, bool have_tab,
                                                 int64_t tab_stride, TInsn &t)
 {
     const uint32_t op = w & 0xffu, a = (w >> 8) & 0xffu, b = w >> 16;
+    const double kb = b < nk ? sconst[b] : __longlong_as_double(0x7ff8000000000000ll);
     const uint32_t mods = (a & 3u) | (((a >> 2) & 3u) << 10);          // SRCX, PUSH, push slot << 10
     uint32_t pf = 0;
     t.h = TH_END;
@@ -479,7 +481,7 @@ __device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__rest
     if (op >= CL_NEG && op <= CL_ABS) {
         const uint32_t f = closyr_th_of_function[op - CL_NEG];
         if (op == CL_POWC) {
-            t.c = sconst[b];
+            t.c = kb;
             if (nonfinite(t.c) || t.c == 0.0) pf = PF_NO_FAST;
         }
         if ((a & CL_M_SRCX) && have_tab && op >= CL_RECIP && op <= CL_ACOS && ((VM_TAB_MASK >> (op - CL_RECIP)) & 1u)) {
@@ -498,13 +500,13 @@ __device__ __forceinline__ uint32_t decode_insn(uint32_t w, const double *__rest
     switch (op) {
     case CL_END: break;
     case CL_LDX: t.h = (a & CL_M_PUSH) ? TH_LDXP : TH_LDX; t.aux = mods & ~1u; break;
-    case CL_LDC: t.h = (a & CL_M_PUSH) ? TH_LDCP : TH_LDC; t.aux = mods & ~1u; t.c = sconst[b]; break;
-    case CL_LDZ: t.h = TH_LDZ; pf = PF_NO_FAST; break;
+    case CL_LDC: t.h = (a & CL_M_PUSH) ? TH_LDCP : TH_LDC; t.aux = mods & ~1u; t.c = kb; break;
+    case CL_LDZ: t.h = b + 1u < nk ? TH_LDZ : TH_LDSPEC; if (t.h == TH_LDSPEC) t.aux = 1u << 16; pf = PF_NO_FAST; break;
     case CL_LDSPEC: t.h = TH_LDSPEC; t.aux = a << 16; pf = PF_NO_FAST; break;
     case CL_ADDX: t.h = TH_ADDX; break;
-    case CL_ADDC: t.h = TH_ADDC; t.c = sconst[b]; break;
+    case CL_ADDC: t.h = TH_ADDC; t.c = kb; break;
     case CL_MULX: t.h = TH_MULX; break;
-    case CL_MULC: t.h = TH_MULC; t.c = sconst[b]; break;
+    case CL_MULC: t.h = TH_MULC; t.c = kb; break;
     default:                                        // unknown opcode: stays symbolic in Symja, never a real number
         t.h = TH_LDSPEC;
         t.aux = 1u << 16;
@@ -953,7 +955,7 @@ __device__ __noinline__ Z zrsqrt(Z a) { return zrecip(zsqrt(a)); }
 // nonreal = the mask of points whose value is NOT a real number (eval.clj:70-80 turns those into +Inf).
 // `tab` = base of the f(x_i) tables (or nullptr), idx[j] = the point's index.  Must be called by whole warps.
 template <int P> struct CplxArgs { int64_t idx[P]; };
-template <int P> struct CplxResult { double out[P]; uint32_t nonreal; };
+template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real; };   // left_real: the warp left real mode at some instruction
 
 // The cheap handlers of REAL MODE in PTX, two points per lane (the structure of run_real's block; see there).
 // Operands: %0 %1 the real parts, %2 ip, %3 sm (bit k = slot k holds imaginary parts), %4..%7 = h aux c.lo c.hi of the
@@ -1030,11 +1032,12 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
     Z deep[NDEEP][P];                                        // local memory (DEEP only)
     uint32_t cmo = 0;                                        // 0 real mode, TH_COUNT complex mode
     uint32_t sm = 0;                                         // slots holding imaginary parts
+    uint32_t left = 0;                                       // complex mode was entered at least once
     uint32_t ip = tcode_addr;
     double x[P];
     CLOSYR_FORJ { x[j] = ldg_f64(xs + idx[j]); a.re[j] = 0.0; a.im[j] = 0.0; }
     const double *const tp0 = tab + idx[0], *const tp1 = tab + idx[1];      // never dereferenced without tables
-#define CLOSYR_TO_COMPLEX() { CLOSYR_FORJ a.im[j] = 0.0; cmo = TH_COUNT; }
+#define CLOSYR_TO_COMPLEX() { CLOSYR_FORJ a.im[j] = 0.0; cmo = TH_COUNT; left = 1u; }
 #define CLOSYR_STORE(k_)                                                                    \
     {                                                                                       \
         const uint32_t k = (k_);                                                            \
@@ -1111,6 +1114,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_END + TH_COUNT: {
             CplxResult<P> res;
             res.nonreal = 0;
+            res.left_real = left;
             CLOSYR_FORJ {
                 const bool real = a.re[j] == a.re[j] && (cmo == 0 || a.im[j] == 0.0);
                 if (!real) res.nonreal |= 1u << j;
@@ -1161,6 +1165,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             const Z z = zmk(sconst[aux >> 16], sconst[(aux >> 16) + 1]);
             CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
             cmo = TH_COUNT;
+            left = 1u;
             break;
         }
         case TH_LDSPEC:
@@ -1168,6 +1173,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             const Z z = (aux >> 16) == 0 ? zcinf() : zindet();
             CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
             cmo = TH_COUNT;
+            left = 1u;
             break;
         }
         // ---- real mode: IEEE arithmetic is the algebra
