@@ -83,7 +83,6 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     DevBuf xs, ys, leaf_tab, scores, rflags, partials, partials_all, flush, eval_xs, eval_f, eval_status, rank_a, rank_b;
-    DevBuf csum, cmax, worklist;          // hand-over between the two scoring kernels (kernels.cuh ScoreParams)
     int64_t leaf_stride = 0;
     DevPop pop, eval_pop;
     int64_t chunk_lo = 0, chunk_hi = 0;   // point-sharded mode: this device's chunk range
@@ -209,7 +208,7 @@ int check_population(closyr_ctx *ctx, const closyr_population *pop)
 // tile size (in chunks, power of two) so that the launch has enough warps to fill the GPU
 int32_t pick_chunks_per_tile(int64_t n_expr, int64_t nchunks)
 {
-    const int64_t target_items = 148 * 16;             // CTAs of 8 warps, 4 resident per SM, a few waves
+    const int64_t target_items = 148 * 6;              // CTAs of up to 32 warps, 1 resident per SM, a few waves
     int64_t cpt = pow2_ceil(std::max<int64_t>(1, nchunks));
     while (cpt > MAX_CHUNKS_PER_TILE) cpt >>= 1;
     while (cpt > 4 && n_expr * ((nchunks + cpt - 1) / cpt) < target_items) cpt >>= 1;
@@ -249,14 +248,6 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.partials = nullptr;
     sp.partial_tile_offset = 0;
     if (ne * n_tiles > 0x7fffffff) return fail(ctx, CLOSYR_E_ARG, "too many (expression, tile) items for one launch");
-    const size_t n_items = (size_t)ne * n_tiles;
-    CU(ctx, d.csum.reserve(n_items * cpt * 8));
-    CU(ctx, d.cmax.reserve(n_items * 8));
-    CU(ctx, d.worklist.reserve(n_items * 4 + 16));
-    sp.csum = (double *)d.csum.p;
-    sp.cmax = (double *)d.cmax.p;
-    sp.wl_count = (uint32_t *)d.worklist.p;
-    sp.worklist = (uint32_t *)d.worklist.p + 4;
     const bool direct = want_final && n_tiles == 1;
     sp.final_scores = direct ? 1 : 0;
     if (!direct) {
@@ -349,7 +340,7 @@ void closyr_ctx_destroy(closyr_ctx *ctx)
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.xs, &d.ys, &d.leaf_tab, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
-                           &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b, &d.csum, &d.cmax, &d.worklist })
+                           &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b })
             b->release();
         d.pop.release();
         d.eval_pop.release();

@@ -23,9 +23,7 @@ using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_LEVELS = 40;
-constexpr int FAST_MAX_WARPS = 16;   // score_fast_kernel: warps per CTA (runtime, power of two, default 8)
-constexpr int FAST_MIN_CTAS = 2;     // per SM at the largest CTA: 64 registers per thread
-constexpr int SLOW_WARPS = 32;       // score_slow_kernel: one CTA per SM, one program per SM
+constexpr int MAX_SCORE_WARPS = 32;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
 
 __device__ __forceinline__ double warp_sum(double s)
 {
@@ -393,31 +391,22 @@ __device__ __forceinline__ void tree_reduce_chunks(double *slvl, int cnt, int la
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Scoring is two kernels.
-//
-// score_fast_kernel: one small CTA per (expression, tile of points), several CTAs per SM.  The program's threaded code
-// arrives with ONE TMA bulk copy; after that the warps are on their own: each takes the tile's 128-point chunks from a
-// shared counter and runs the IEEE-real fast pass on them.  The only CTA barriers are the one before the first chunk and
-// the one before the reduction, and one CTA's staging and reduction overlap the other CTAs' arithmetic.  The fast
-// interpreter is compact enough for the SM's instruction cache to hold what warps of DIFFERENT programs execute.  A
-// chunk in which some point was reported (it left the real line, or met an infinity) is only marked; a tile with marked
-// chunks leaves its chunk sums in global memory and queues itself for the second kernel.
-//
-// score_slow_kernel: one CTA of 32 warps per queued tile, ONE program per SM, the warps move through the rounds in
-// step (fast pass again on the marked chunks, CTA-wide compaction of the reported points, complete algebra).  The
-// complete-algebra interpreter and the complex functions behind it are ~150 KB of code: warps that sit in different
-// places of it (different programs on one SM, or one program without the round structure) spend most of their time
-// waiting for instructions (measured: 47 stalled warp-cycles per issued instruction on `no_instruction`).
+// score_kernel: one CTA of up to 32 warps per (expression, tile of points), ONE program per SM.  The program's threaded
+// code (made once per upload by prepare_kernel) arrives with one TMA bulk copy.  The warps move through the tile in
+// rounds of one 128-point chunk per warp: fast pass, CTA-wide compaction of the reported points, complete algebra.
+// Why one program per SM and rounds in step: the complete-algebra interpreter and the complex functions behind it are
+// ~150 KB of code.  Measured in r02 (profiles/r02_design_experiments.md): warps that sit in different places of it --
+// several programs per SM, or one program whose warps take chunks on their own -- wait for instructions most of the
+// time (47 stalled warp-cycles per issued instruction on `no_instruction`); only the fast interpreter is small enough
+// for that, and a fast-only kernel in front of this one did not pay for the second pass over the marked chunks.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr uint32_t WL_ALL_CHUNKS = 0x80000000u;      // work-list entry: the fast kernel evaluated nothing of this tile
-
-__global__ void __launch_bounds__(FAST_MAX_WARPS * 32, FAST_MIN_CTAS) score_fast_kernel(const ScoreParams p)
+__global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const ScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_max[FAST_MAX_WARPS];
-    __shared__ uint32_t s_marked[FAST_MAX_WARPS];
+    __shared__ double s_max[MAX_SCORE_WARPS];
+    __shared__ uint32_t s_nonreal[MAX_SCORE_WARPS], s_full[MAX_SCORE_WARPS];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_next;
+    __shared__ uint32_t s_counts[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t item = blockIdx.x;
     const int64_t e = item / p.n_tiles;
@@ -441,111 +430,12 @@ __global__ void __launch_bounds__(FAST_MAX_WARPS * 32, FAST_MIN_CTAS) score_fast
         }
         return;
     }
-    if ((flags & CL_F_CONST) || (pflags & PF_NO_FAST)) {
-        // constant expressions and programs the IEEE path cannot express: everything is the second kernel's
-        if (tid == 0) p.worklist[atomicAdd(p.wl_count, 1u)] = (uint32_t)item | WL_ALL_CHUNKS;
-        return;
-    }
 
-    // shared memory: [warp slots | chunk sums | threaded code]
-    double *const slvl = reinterpret_cast<double *>(smem) + nwarps * SLOT_DOUBLES_PER_WARP;
-    TInsn *const tcode = reinterpret_cast<TInsn *>(slvl + ((p.chunks_per_tile + 1) & ~1));
-    if (tid == 0) s_next = 0;
-    stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);
-
-    const uint32_t tcode_addr = smem_u32(tcode);
-    const uint32_t slot_addr = smem_u32(reinterpret_cast<double *>(smem) + warp * SLOT_DOUBLES_PER_WARP + lane);
-    const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
-    int64_t c_hi = c_lo + p.chunks_per_tile;
-    if (c_hi > p.chunk_end) c_hi = p.chunk_end;
-    const int cnt = (int)(c_hi - c_lo);
-    const uint32_t slvl_addr = smem_u32(slvl);
-    double warp_mx = 0.0;
-    uint32_t marked = 0;
-    for (;;) {
-        int ci = 0;
-        if (lane == 0) ci = (int)atomicAdd(&s_next, 1u);
-        ci = __shfl_sync(FULL, ci, 0);
-        if (ci >= cnt) break;
-        const int64_t base = (c_lo + ci) * CHUNK_POINTS + lane * POINTS_PER_LANE;
-        // xs, ys and every table row are padded to whole chunks (x = 1.0, y = 0.0), so a lane always loads its 4 points
-        const int64_t left = p.n - base;
-        const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
-        const uint32_t sum_addr = slvl_addr + (uint32_t)ci * 8u;
-        const RealResult<4> rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
-        if (__any_sync(FULL, rr.ev != 0)) {
-            marked = 1;
-            if (lane == 0) sts_f64(sum_addr, __longlong_as_double(0x7ff8000000000000ll));     // a sum of residuals is never NaN
-        } else warp_mx = max_nonneg(warp_mx, rr.mx);
-    }
-    warp_mx = warp_max_nonneg(warp_mx);
-    if (lane == 0) { s_max[warp] = warp_mx; s_marked[warp] = marked; }
-    __syncthreads();
-    if (warp != 0) return;
-    const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
-    const uint32_t tile_marked = __reduce_or_sync(FULL, lane < nwarps ? s_marked[lane] : 0u);
-    if (tile_marked) {
-        double *out = p.csum + item * p.chunks_per_tile;
-        for (int i = lane; i < cnt; i += 32) out[i] = slvl[i];
-        if (lane == 0) {
-            p.cmax[item] = tile_max;
-            __threadfence();
-            p.worklist[atomicAdd(p.wl_count, 1u)] = (uint32_t)item;
-        }
-        return;
-    }
-    tree_reduce_chunks(slvl, cnt, lane);
-    if (lane == 0) emit_tile(p, e, tile, leafs, false, cnt > 0 ? slvl[0] : 0.0, tile_max, 0u, false);
-}
-
-__global__ void __launch_bounds__(SLOW_WARPS * 32, 1) score_slow_kernel(const ScoreParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_max[SLOW_WARPS];
-    __shared__ uint32_t s_nonreal[SLOW_WARPS], s_full[SLOW_WARPS];
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_counts[64];
-    __shared__ int s_nmarked;
-    if (blockIdx.x >= *p.wl_count) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t wl = p.worklist[blockIdx.x];
-    const bool all_chunks = (wl & WL_ALL_CHUNKS) != 0;
-    const int64_t item = wl & ~WL_ALL_CHUNKS;
-    const int64_t e = item / p.n_tiles;
-    const int tile = (int)(item - e * p.n_tiles);
-    const uint4 dq = __ldg(reinterpret_cast<const uint4 *>(p.pop.desc + e));
-    const uint32_t ncode = dq.y & 0xffffu, pflags = dq.y >> 16, meta = dq.z;
-    const int leafs = (int)(meta & 0xffffu);
-    const uint32_t flags = (meta >> 16) & 0xffu;
-
-    // shared memory: [warp slots | compaction list | chunk sums | marked chunks (u16) | threaded code]
+    // shared memory: [warp slots | compaction list | chunk sums (+ a scratch word) | threaded code]
     double *const list = reinterpret_cast<double *>(smem) + nwarps * SLOT_DOUBLES_PER_WARP;
     double *const slvl = list + nwarps * CHUNK_POINTS;
-    uint16_t *const chunks = reinterpret_cast<uint16_t *>(slvl + ((p.chunks_per_tile + 2) & ~1));
-    TInsn *const tcode = reinterpret_cast<TInsn *>(reinterpret_cast<unsigned char *>(chunks) + ((p.chunks_per_tile * 2 + 15) & ~15));
-    const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
-    int64_t c_hi = c_lo + p.chunks_per_tile;
-    if (c_hi > p.chunk_end) c_hi = p.chunk_end;
-    const int cnt = (int)(c_hi - c_lo);
-    // the fast kernel's chunk sums; NaN marks the chunks it left to this kernel
-    if (!all_chunks) {
-        const double *in = p.csum + item * p.chunks_per_tile;
-        for (int i = tid; i < cnt; i += blockDim.x) slvl[i] = in[i];
-    }
-    stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);       // contains the barrier after the loads above
-    if (warp == 0) {
-        int n = 0;
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-            const int c = c0 + lane;
-            const bool m = c < cnt && (all_chunks || slvl[c] != slvl[c]);
-            const uint32_t mask = __ballot_sync(FULL, m);
-            if (m) chunks[n + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)c;
-            n += __popc(mask);
-        }
-        if (lane == 0) s_nmarked = n;
-    }
-    __syncthreads();
-    const int nmarked = s_nmarked;
+    TInsn *const tcode = reinterpret_cast<TInsn *>(slvl + ((p.chunks_per_tile + 2) & ~1));
+    stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);
 
     const double *const sconst = p.pop.consts + dq.w;
     const uint32_t tcode_addr = smem_u32(tcode);
@@ -556,18 +446,22 @@ __global__ void __launch_bounds__(SLOW_WARPS * 32, 1) score_slow_kernel(const Sc
         const uint32_t aux = p.pop.aux[e];
         if ((aux >> 16) != 0 && (int64_t)(aux >> 16) == p.n) quirk_off_plus1 = (aux & 0xffffu) + 1u;
     }
+    const int64_t c_lo = p.chunk_begin + (int64_t)tile * p.chunks_per_tile;
+    int64_t c_hi = c_lo + p.chunks_per_tile;
+    if (c_hi > p.chunk_end) c_hi = p.chunk_end;
+    const int cnt = (int)(c_hi - c_lo);
     const uint32_t slvl_addr = smem_u32(slvl);
     const bool fast_ok = !is_const && !(pflags & PF_NO_FAST);
     double warp_mx = 0.0;
     uint32_t nonreal = 0, mode = 0, parity = 0, used_full = 0;
-    for (int r0 = 0; r0 < nmarked; r0 += nwarps, parity ^= 1u) {
-        const bool have = r0 + warp < nmarked;
-        const int ci = have ? (int)chunks[r0 + warp] : 0;
+    for (int r0 = 0; r0 < cnt; r0 += nwarps, parity ^= 1u) {
+        const int ci = r0 + warp;
+        const bool have = ci < cnt;
         const int64_t base = (c_lo + ci) * CHUNK_POINTS + lane * POINTS_PER_LANE;
+        // xs, ys and every table row are padded to whole chunks (x = 1.0, y = 0.0), so a lane always loads its 4 points
         const int64_t left = have ? p.n - base : 0;
         const uint32_t valid = left >= 4 ? 0xfu : (left <= 0 ? 0u : (1u << (int)left) - 1u);
-        // an idle warp's sum goes to the scratch word behind the chunk sums
-        const uint32_t sum_addr = slvl_addr + (uint32_t)(have ? ci : p.chunks_per_tile) * 8u;
+        const uint32_t sum_addr = slvl_addr + (uint32_t)(have ? ci : p.chunks_per_tile) * 8u;      // idle warps: the scratch word
         const bool fast = fast_ok && mode == 0;
         RealResult<4> rr;
         rr.ev = valid;
@@ -575,6 +469,11 @@ __global__ void __launch_bounds__(SLOW_WARPS * 32, 1) score_slow_kernel(const Sc
         rr.v[0] = rr.v[1] = rr.v[2] = rr.v[3] = 0.0;
         if (fast && have)
             rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+        // nothing reported anywhere in the CTA (the common round): one barrier, the fast pass has done everything
+        if (fast && !__syncthreads_or(rr.ev != 0)) {
+            warp_mx = max_nonneg(warp_mx, rr.mx);
+            continue;
+        }
         const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
                                               base, valid, rr.ev, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
@@ -588,11 +487,10 @@ __global__ void __launch_bounds__(SLOW_WARPS * 32, 1) score_slow_kernel(const Sc
     __syncthreads();
     if (warp != 0) return;
     tree_reduce_chunks(slvl, cnt, lane);
-    double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
+    const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
     const uint32_t tile_nonreal = __reduce_add_sync(FULL, lane < nwarps ? s_nonreal[lane] : 0u);
     const uint32_t tile_full = __reduce_or_sync(FULL, lane < nwarps ? s_full[lane] : 0u);
     if (lane != 0) return;
-    if (!all_chunks) tile_max = max_nonneg(tile_max, p.cmax[item]);
     emit_tile(p, e, tile, leafs, is_const && !quirk_off_plus1 && tile_nonreal != 0, cnt > 0 ? slvl[0] : 0.0, tile_max, tile_nonreal, tile_full != 0);
 }
 
@@ -790,17 +688,13 @@ int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream)
 {
     const int64_t items = p.pop.n_expr * p.n_tiles;
     if (items <= 0) return 0;
+    // [warp slots | compaction list | chunk sums + a scratch word | threaded code + the entry the dispatch loop prefetches past END]
+    const size_t smem = (size_t)p.warps * (SLOT_DOUBLES_PER_WARP + CHUNK_POINTS) * 8 + (size_t)((p.chunks_per_tile + 2) & ~1) * 8 +
+                        ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
     // opt in to > 48 KiB of dynamic shared memory; the attribute is per device, so it is set at every launch
-    const size_t smem_fast = (size_t)p.warps * SLOT_DOUBLES_PER_WARP * 8 + (size_t)((p.chunks_per_tile + 1) & ~1) * 8 +
-                             ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
-    const size_t smem_slow = (size_t)SLOW_WARPS * (SLOT_DOUBLES_PER_WARP + CHUNK_POINTS) * 8 + (size_t)((p.chunks_per_tile + 2) & ~1) * 8 +
-                             (size_t)((p.chunks_per_tile * 2 + 15) & ~15) + ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
-    if (smem_fast > 48 * 1024) cudaFuncSetAttribute(score_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
-    cudaFuncSetAttribute(score_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slow);
-    cudaMemsetAsync(p.wl_count, 0, sizeof(uint32_t), (cudaStream_t)stream);
-    score_fast_kernel<<<(unsigned)items, p.warps * 32, smem_fast, (cudaStream_t)stream>>>(p);
-    score_slow_kernel<<<(unsigned)items, SLOW_WARPS * 32, smem_slow, (cudaStream_t)stream>>>(p);
-    return 2;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    score_kernel<<<(unsigned)items, p.warps * 32, smem, (cudaStream_t)stream>>>(p);
+    return 1;
 }
 
 void launch_finalize(const FinalizeParams &p, void *stream)
@@ -833,11 +727,11 @@ size_t eval_smem_bytes(uint32_t max_code_words)
 }
 int score_warps(int32_t chunks_per_tile)
 {
-    // CLOSYR_SCORE_WARPS (a power of two <= 16) sets the CTA size: a tuning knob for measurements, not an API
+    // CLOSYR_SCORE_WARPS (a power of two <= 32) caps the CTA size: a tuning knob for measurements, not an API
     static const int cap = [] {
         const char *e = getenv("CLOSYR_SCORE_WARPS");
         const int v = e ? atoi(e) : 0;
-        return (v >= 1 && v <= FAST_MAX_WARPS && (v & (v - 1)) == 0) ? v : 8;
+        return (v >= 1 && v <= MAX_SCORE_WARPS && (v & (v - 1)) == 0) ? v : MAX_SCORE_WARPS;
     }();
     int w = 1;
     while (w < cap && w < chunks_per_tile) w <<= 1;

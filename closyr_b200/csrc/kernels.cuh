@@ -62,11 +62,6 @@ struct ScoreParams {
     // `leaf_stride` doubles; nullptr = compute in the kernel
     const double *leaf_tab;
     int64_t leaf_stride;
-    // hand-over from score_fast_kernel to score_slow_kernel (device scratch owned by the context)
-    double *csum;                     // [items][chunks_per_tile] chunk sums of the queued tiles, NaN = chunk left to the slow kernel
-    double *cmax;                     // [items] largest residual of the chunks the fast kernel finished
-    uint32_t *worklist;               // [items] queued (expression, tile) items
-    uint32_t *wl_count;               // number of queued items (zeroed by launch_score)
 };
 
 constexpr int LEAF_TAB_ROWS = CL_ACOS - CL_RECIP + 1;
