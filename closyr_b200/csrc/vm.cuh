@@ -547,6 +547,11 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v)
     asm volatile("" : "+r"(v));
     return v;
 }
+__device__ __forceinline__ double opaque(double v)
+{
+    asm volatile("" : "+d"(v));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_insn(uint32_t addr)          // the threaded code is read-only while it runs
 {
     uint4 v;
@@ -585,6 +590,19 @@ template <int P> __device__ __forceinline__ uint32_t mask_nonfinite(const double
     CLOSYR_FORJ if (nonfinite(a[j])) m |= 1u << j;
     return m;
 }
+// NaN as the arithmetic and the math routines produce it (quiet); infinities
+template <int P> __device__ __forceinline__ uint32_t mask_nan(const double (&a)[P])
+{
+    uint32_t m = 0;
+    CLOSYR_FORJ if (abs_hi(a[j]) >= 0x7ff80000u) m |= 1u << j;
+    return m;
+}
+template <int P> __device__ __forceinline__ uint32_t mask_inf(const double (&a)[P])
+{
+    uint32_t m = 0;
+    CLOSYR_FORJ if (is_inf(a[j])) m |= 1u << j;
+    return m;
+}
 template <int P> __device__ __forceinline__ bool every_point_nan(const double (&a)[P])
 {
     bool all = true;
@@ -618,12 +636,14 @@ template <int P> __device__ __forceinline__ void f_tabulated(uint32_t op, double
 //   v finite, no report  <=>  s is a finite real and v == s;
 //   v = +-Inf            =>   s is ComplexInfinity, a directed infinity or Indeterminate (never a finite number;
 //                             the residual is max-resid either way, ops.clj:78-90)
-//   v NaN                =>   reported: NaN is absorbing through every instruction of this path, so a domain exit
-//                             (the algebra continues over the complex numbers) or an IEEE invalid operation
-//                             anywhere in the program shows in the result.
-// The returned mask has bit j set when point j must be re-evaluated with the complete algebra: its result is NaN,
-// or an instruction that maps an infinity to a finite number (1/Inf, E^-Inf, Inf^-k) was handed a non-finite
-// operand -- whether that is right depends on which infinity it was.
+//   v NaN                =>   either the point left a function's real domain somewhere (the algebra continues over the
+//                             complex numbers: reported), or the NaN was made by arithmetic on infinities / NaNs and s is
+//                             Indeterminate, which absorbs everything that follows (not reported: never a real number).
+//                             NaN is absorbing through every instruction of this path, so either shows in the result.
+// The returned mask has bit j set when point j must be re-evaluated with the complete algebra: its result is NaN after
+// a domain exit, or an instruction that maps an infinity to a finite number (E^-Inf, Inf^-k) or whose result depends on
+// the kind of infinity was handed one -- IEEE cannot tell ComplexInfinity from a directed infinity, nor from an
+// Indeterminate the algebra reached earlier (ComplexInfinity + ComplexInfinity).
 // Programs with PF_NO_FAST never come here.
 // ------------------------------------------------------------------------------------------------
 // A function of its own (not inlined into the kernel): the dispatch loop gets a register allocation of its own.
@@ -758,7 +778,8 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
     static_assert(P == 4, "slot stride and x loads are written for 4 points per lane");
     RealResult<P> res;
     double (&acc)[P] = res.v;
-    uint32_t ev = 0;
+    uint32_t ev = 0;                 // points handed an infinity where its kind matters
+    uint32_t dx = 0;                 // points that left a function's real domain (their NaN is not an Indeterminate)
     uint32_t ip = tcode_addr;
     double x[P];
     ldg_x(xp, x);
@@ -767,6 +788,23 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
     if (aux & 2u) {                                                            \
         const uint32_t sl_ = slot_addr + (aux & 0xc00u);                       \
         CLOSYR_FORJ sts_f64(sl_ + j * 256, acc[j]);                            \
+    }
+    // A function with a real domain: a NaN it makes out of a number is a domain exit (the algebra continues over the complex
+    // numbers, only run_cplx knows the value); every other NaN of this path comes from arithmetic on infinities (Inf - Inf,
+    // 0 * Inf, Sin(Inf) ...) or from a NaN, and stands for Indeterminate, which absorbs every later operation: such a point
+    // is not a real number whatever follows (residual max-resid, ops.clj:78-90) and needs no second evaluation.
+    // Points are sorted by x, so a domain exit usually takes whole chunks: once every point of the warp is NaN the rest of
+    // the pass cannot change anything.
+#define CLOSYR_DOMAIN(body_)                                                                        \
+    {                                                                                               \
+        const uint32_t pre_ = mask_nan<P>(acc);                                                     \
+        body_;                                                                                      \
+        dx |= mask_nan<P>(acc) & ~pre_;                                                             \
+        if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) {                                     \
+            res.ev = (ev | dx) & valid;                                                             \
+            res.mx = chunk_residuals(acc, yp, valid, sum_addr);                                     \
+            return res;                                                                             \
+        }                                                                                           \
     }
 #pragma unroll 1
     for (;;) {
@@ -789,8 +827,7 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
     redo:
         switch (h) {
         case TH_END: {
-            CLOSYR_FORJ if (acc[j] != acc[j]) ev |= 1u << j;
-            res.ev = ev & valid;
+            res.ev = (ev | (dx & mask_nan<P>(acc))) & valid;
             res.mx = chunk_residuals(acc, yp, valid, sum_addr);     // overwritten by the slow path when a point was reported
             return res;
         }
@@ -800,7 +837,12 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
             // the warp is lost the rest of the fast pass is wasted work (the complete algebra starts over anyway)
             CLOSYR_PUSH_IF()
             ldg_x(reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c)), acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
+            dx |= mask_nan<P>(acc);                          // x is a number: a NaN entry is a domain exit
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) {
+                res.ev = (ev | dx) & valid;
+                res.mx = chunk_residuals(acc, yp, valid, sum_addr);
+                return res;
+            }
             break;
         }
         case TH_MOD:                                         // PUSH / SRCX modifiers of a function that has no table
@@ -811,49 +853,30 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         case TH_NEG: CLOSYR_FORJ acc[j] = -acc[j]; break;      // reached through TH_MOD only
         case TH_SQR: CLOSYR_FORJ acc[j] = acc[j] * acc[j]; break;
         case TH_ABS: CLOSYR_FORJ acc[j] = fabs(acc[j]); break;
-        case TH_RECIP: ev |= mask_nonfinite<P>(acc); f_recip<P>(acc); break;
-        case TH_SQRT:
-            f_sqrt<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
-        case TH_RSQRT:
-            ev |= mask_nonfinite<P>(acc);
-            f_rsqrt<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
+        case TH_RECIP: ev |= mask_inf<P>(acc); f_recip<P>(acc); break;
+        case TH_SQRT: CLOSYR_DOMAIN(f_sqrt<P>(acc)) break;
+        case TH_RSQRT: ev |= mask_inf<P>(acc); CLOSYR_DOMAIN(f_rsqrt<P>(acc)) break;
         case TH_POWI: {
             const int n = (int)(short)(aux >> 16);
             if (n < 0) {
-                ev |= mask_nonfinite<P>(acc);
+                ev |= mask_inf<P>(acc);
                 f_powu<P>(acc, (unsigned)-n);
                 f_recip<P>(acc);
             } else f_powu<P>(acc, (unsigned)n);
             break;
         }
-        case TH_POWC:
-            ev |= mask_nonfinite<P>(acc);
-            f_powc<P>(acc, c);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
-        case TH_EXP: ev |= mask_nonfinite<P>(acc); v_exp<P>(acc); break;
-        case TH_LOG:
-            v_log<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
+        case TH_POWC: ev |= mask_inf<P>(acc); CLOSYR_DOMAIN(f_powc<P>(acc, c)) break;
+        case TH_EXP: ev |= mask_inf<P>(acc); v_exp<P>(acc); break;
+        case TH_LOG: CLOSYR_DOMAIN(v_log<P>(acc)) break;
         case TH_SIN: v_sin<P>(acc); break;
         case TH_COS: v_cos<P>(acc); break;
         case TH_TAN: f_tan<P>(acc); break;
-        case TH_ASIN:
-            f_asin<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
-        case TH_ACOS:
-            f_acos<P>(acc);
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) { res.ev = ALL & valid; res.mx = 0.0; return res; }
-            break;
+        case TH_ASIN: CLOSYR_DOMAIN(f_asin<P>(acc)) break;
+        case TH_ACOS: CLOSYR_DOMAIN(f_acos<P>(acc)) break;
         default: { res.ev = ALL & valid; res.mx = 0.0; return res; }                 // LDZ LDSPEC POWS: PF_NO_FAST programs do not come here
         }
     }
+#undef CLOSYR_DOMAIN
 #undef CLOSYR_PUSH_IF
 }
 #undef CLOSYR_CHEAP_HANDLERS
@@ -1050,7 +1073,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             CLOSYR_FORJ deep[DEEP ? k - CLOSYR_REG_SLOTS : 0][j] = zv(a.re[j], cmo ? a.im[j] : 0.0); \
         }                                                                                   \
     }
-#define CLOSYR_PUSH_IF() if (aux & 2u) CLOSYR_STORE((aux >> 10) & 3u)
+#define CLOSYR_PUSH_IF() { const uint32_t ax_ = AUX; if (ax_ & 2u) CLOSYR_STORE((ax_ >> 10) & 3u) }
 #define CLOSYR_LOADX(dst) CLOSYR_FORJ dst[j] = x[j];
     // loads slot k into (sre, sim); `scx` = the slot may hold imaginary parts
 #define CLOSYR_LOAD(k_)                                                                     \
@@ -1079,6 +1102,11 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         h += TH_COUNT;                                                                      \
         goto redo;                                                                          \
     }
+    // AUX / CC: the operand word / literal as the handler sees it.  Through an opaque copy, otherwise the compiler hoists
+    // every handler's decoding of them (slot masks, exponents, table addresses) to the head of the dispatch loop:
+    // 42 instructions per dispatch in r02b's profile
+#define AUX opaque(aux)
+#define CC opaque(c)
 #pragma unroll 1
     for (;;) {
         uint32_t h, aux, clo, chi;
@@ -1142,7 +1170,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_TABRP + TH_COUNT:
         case TH_TABC + TH_COUNT: {
             CLOSYR_PUSH_IF()
-            const double *row = reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c));
+            const double *row = reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(opaque(c)));
             double t[P];
             bool fin = true;
             CLOSYR_FORJ { t[j] = row[idx[j]]; fin = fin && !nonfinite(t[j]); }
@@ -1151,18 +1179,18 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             // some point is off the function's real domain (or at a pole): the function itself, complex mode
             CLOSYR_LOADX(a.re)
             CLOSYR_TO_COMPLEX()
-            h = ((aux >> 2) & 0xffu) + TH_COUNT;
+            h = ((AUX >> 2) & 0xffu) + TH_COUNT;
             goto redo;
         }
         case TH_MOD:
         case TH_MOD + TH_COUNT:
             CLOSYR_PUSH_IF()
-            if (aux & 1u) { CLOSYR_LOADX(a.re) cmo = 0; }
-            h = ((aux >> 2) & 0xffu) + cmo;
+            if (AUX & 1u) { CLOSYR_LOADX(a.re) cmo = 0; }
+            h = ((AUX >> 2) & 0xffu) + cmo;
             goto redo;
         case TH_LDZ:
         case TH_LDZ + TH_COUNT: {
-            const Z z = zmk(sconst[aux >> 16], sconst[(aux >> 16) + 1]);
+            const Z z = zmk(sconst[AUX >> 16], sconst[(AUX >> 16) + 1]);
             CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
             cmo = TH_COUNT;
             left = 1u;
@@ -1170,7 +1198,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         }
         case TH_LDSPEC:
         case TH_LDSPEC + TH_COUNT: {
-            const Z z = (aux >> 16) == 0 ? zcinf() : zindet();
+            const Z z = (AUX >> 16) == 0 ? zcinf() : zindet();
             CLOSYR_FORJ { a.re[j] = z.re; a.im[j] = z.im; }
             cmo = TH_COUNT;
             left = 1u;
@@ -1185,10 +1213,10 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_SQR: CLOSYR_FORJ a.re[j] = a.re[j] * a.re[j]; break;
         case TH_ABS: CLOSYR_FORJ a.re[j] = fabs(a.re[j]); break;
         case TH_ST:
-        case TH_ST + TH_COUNT: CLOSYR_STORE(aux >> 10) break;
+        case TH_ST + TH_COUNT: CLOSYR_STORE(AUX >> 10) break;
         case TH_ADDS:
         case TH_MULS: {
-            const uint32_t k = aux >> 10;
+            const uint32_t k = AUX >> 10;
             const bool scx = (DEEP && k >= CLOSYR_REG_SLOTS) || ((sm >> k) & 1u);
             if (scx) {
                 CLOSYR_TO_COMPLEX()
@@ -1204,7 +1232,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_SQRT: CLOSYR_REALF(!(x_ < 0.0), f_sqrt<P>(a.re))
         case TH_RSQRT: CLOSYR_REALF(!(x_ <= 0.0), f_rsqrt<P>(a.re))
         case TH_POWI: {
-            const int n = (int)(short)(aux >> 16);
+            const int n = (int)(short)(AUX >> 16);
             double r[P];
             CLOSYR_FORJ r[j] = a.re[j];
             f_powu<P>(r, (unsigned)(n < 0 ? -n : n));
@@ -1216,7 +1244,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
             h += TH_COUNT;
             goto redo;
         }
-        case TH_POWC: CLOSYR_REALF(x_ > 0.0 && !is_inf(x_) && !nonfinite(c) && c != 0.0, f_powc<P>(a.re, c))
+        case TH_POWC: CLOSYR_REALF(x_ > 0.0 && !is_inf(x_) && !nonfinite(CC) && CC != 0.0, f_powc<P>(a.re, c))
         case TH_EXP: v_exp<P>(a.re); break;
         case TH_LOG: CLOSYR_REALF(!(x_ <= 0.0), v_log<P>(a.re))
         case TH_SIN: v_sin<P>(a.re); break;
@@ -1233,10 +1261,10 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_NEG + TH_COUNT: CLOSYR_ZCALL(zneg) break;
         case TH_SQR + TH_COUNT: { double sr[P], si[P]; CLOSYR_FORJ { sr[j] = a.re[j]; si[j] = a.im[j]; } c_mul<P>(a, sr, si); break; }
         case TH_ABS + TH_COUNT: CLOSYR_ZCALL(zabs) break;
-        case TH_ADDS + TH_COUNT: { CLOSYR_LOAD(aux >> 10) (void)scx; c_add<P>(a, sre, sim); break; }
-        case TH_MULS + TH_COUNT: { CLOSYR_LOAD(aux >> 10) (void)scx; c_mul<P>(a, sre, sim); break; }
+        case TH_ADDS + TH_COUNT: { CLOSYR_LOAD(AUX >> 10) (void)scx; c_add<P>(a, sre, sim); break; }
+        case TH_MULS + TH_COUNT: { CLOSYR_LOAD(AUX >> 10) (void)scx; c_mul<P>(a, sre, sim); break; }
         case TH_POWS + TH_COUNT: {
-            CLOSYR_LOAD(aux >> 10)
+            CLOSYR_LOAD(AUX >> 10)
             (void)scx;
             CLOSYR_FORJ {
                 const Z r = zpow(zv(sre[j], sim[j]), zv(a.re[j], a.im[j]));
@@ -1249,7 +1277,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         case TH_SQRT + TH_COUNT: CLOSYR_ZCALL(zsqrt) break;
         case TH_RSQRT + TH_COUNT: CLOSYR_ZCALL(zrsqrt) break;
         case TH_POWI + TH_COUNT: {
-            const int n = (int)(short)(aux >> 16);
+            const int n = (int)(short)(AUX >> 16);
             CLOSYR_FORJ {
                 const Z r = zpowi_any(zv(a.re[j], a.im[j]), n);
                 a.re[j] = r.re;
@@ -1280,6 +1308,8 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
         }
         }
     }
+#undef AUX
+#undef CC
 #undef CLOSYR_REALF
 #undef CLOSYR_LOADX
 #undef CLOSYR_LOAD
