@@ -15,6 +15,7 @@ DEFAULT_MAX_LEAFS = 40        # ops.clj:29-31
 
 SHARD_POPULATION = 0
 SHARD_POINTS = 1
+COMM_ID_BYTES = 128
 BUILDER_PINNED = 1
 
 R_TOO_BIG = 0x01
@@ -48,6 +49,7 @@ EXPORTS = [
     "closyr_ctx_create", "closyr_ctx_destroy", "closyr_ctx_device_count", "closyr_set_points",
     "closyr_score_batch", "closyr_upload_population", "closyr_score_resident", "closyr_download_scores",
     "closyr_eval_batch", "closyr_score_from_values", "closyr_rank_resident", "closyr_score_partials_resident", "closyr_finalize_partials",
+    "closyr_comm_unique_id", "closyr_comm_init_rank",
     "closyr_l2_flush", "closyr_fp64_peak_probe", "closyr_kernel_launch_count", "closyr_host_alloc", "closyr_host_free",
     "closyr_selftest_pinned_fallback",
     "closyr_builder_create", "closyr_builder_destroy", "closyr_builder_clear", "closyr_builder_add",
@@ -112,6 +114,8 @@ def lib():
         "closyr_l2_flush": (C.c_int, [vp]),
         "closyr_fp64_peak_probe": (C.c_int, [vp, dp]),
         "closyr_kernel_launch_count": (i64, [vp]),
+        "closyr_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+        "closyr_comm_init_rank": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
         "closyr_host_alloc": (vp, [C.c_size_t]),
         "closyr_host_free": (None, [vp]),
         "closyr_builder_create": (C.c_int, [u32, C.POINTER(vp)]),

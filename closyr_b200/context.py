@@ -110,6 +110,21 @@ class Context:
     def finalize_partials(self, dev_ptr, n_parts, max_leafs):
         L.check(L.lib().closyr_finalize_partials(self._h, C.c_void_p(dev_ptr), n_parts, max_leafs), self._h)
 
+    def init_point_sharding(self, rank, world, dist=None, torch_device=None):
+        """One process per GPU: makes this context (ONE device, shard=SHARD_POINTS) rank `rank` of `world`.  Rank 0
+        creates the NCCL id inside the library, `dist` (torch.distributed, any backend) carries its 128 bytes to the
+        other ranks, every rank joins; afterwards score_resident / score_batch are collective calls and the
+        all-gather of the partial sums is issued by the library on its own stream."""
+        ident = (C.c_uint8 * L.COMM_ID_BYTES)()
+        if rank == 0:
+            L.check(L.lib().closyr_comm_unique_id(ident), self._h)
+        if world > 1:
+            import torch
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=torch_device if dist.get_backend() == "nccl" else "cpu")
+            dist.broadcast(t, src=0)
+            ident = (C.c_uint8 * L.COMM_ID_BYTES)(*t.cpu().tolist())
+        L.check(L.lib().closyr_comm_init_rank(self._h, world, rank, ident), self._h)
+
     def l2_flush(self):
         L.check(L.lib().closyr_l2_flush(self._h), self._h)
 

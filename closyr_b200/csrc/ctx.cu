@@ -4,6 +4,8 @@
 // src/closyr/ops/common.clj:30-76) and the per-phenotype call of ops/score-fn (src/closyr/ops.clj:119-136).
 // There is deliberately no CPU path in this file: without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -35,6 +37,43 @@ void *pinned_alloc(size_t bytes)
 void pinned_free(void *p) { cudaFreeHost(p); }
 
 namespace {
+
+// NCCL is bound at run time (dlopen): the library loads on a box without it, and inside a process that already carries
+// an NCCL (PyTorch) the same copy is used.  Only the entry points of the point-sharding collective are needed.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : { "libnccl.so.2", "libnccl.so" }) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+        a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.handle, "ncclCommInitAll");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.handle, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.handle, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllGather && a.GroupStart && a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
 
 struct DevBuf {                       // grow-only device allocation
     void *p = nullptr;
@@ -86,6 +125,8 @@ struct DeviceState {
     int64_t leaf_stride = 0;
     DevPop pop, eval_pop;
     int64_t chunk_lo = 0, chunk_hi = 0;   // point-sharded mode: this device's chunk range
+    int64_t fin_lo = 0, fin_hi = 0;       // point-sharded mode: the expressions this device finalises and returns
+    ncclComm_t comm = nullptr;            // point-sharded mode: this device's communicator
 };
 
 }  // namespace
@@ -98,6 +139,8 @@ struct closyr_ctx {
     int64_t n_expr = -1;              // resident population size, -1 = none
     bool scored = false;
     int64_t launches = 0;
+    // point sharding across PROCESSES (one device each): this context is rank `rank` of `n_ranks` (closyr_comm_init_rank)
+    int n_ranks = 1, rank = 0;
     std::string err;
     std::mutex mu;
 };
@@ -110,6 +153,13 @@ int fail(closyr_ctx *ctx, int code, const std::string &msg)
     set_error(msg);
     return code;
 }
+
+#define NC(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess)                                                                            \
+            return fail(ctx, CLOSYR_E_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r_));       \
+    } while (0)
 
 #define CU(ctx, call)                                                                                     \
     do {                                                                                                  \
@@ -263,6 +313,7 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
         FinalizeParams fp;
         fp.meta = pv.meta;
         fp.partials = (const double *)d.partials.p;
+        fp.part_stride = ne;
         fp.n_expr = ne;
         fp.n_tiles_total = n_tiles;
         fp.max_leafs = max_leafs;
@@ -322,7 +373,24 @@ int closyr_ctx_create(const int *devices, int n_devices, uint32_t flags, closyr_
         }
     }
     if (ctx->devs.size() > 1 && (flags & CLOSYR_SHARD_POINTS)) {
-        for (size_t i = 1; i < ctx->devs.size(); i++) {       // device 0 gathers the partials over NVLink
+        // the partial residual sums are exchanged with an NCCL all-gather over NVLink: one communicator per device
+        if (!nccl().ok) {
+            closyr_ctx_destroy(ctx);
+            return fail(nullptr, CLOSYR_E_CUDA, "point sharding needs NCCL (libnccl.so.2 not found)");
+        }
+        std::vector<int> devlist;
+        for (auto &d : ctx->devs) devlist.push_back(d.device);
+        std::vector<ncclComm_t> comms(devlist.size(), nullptr);
+        ncclResult_t r = nccl().CommInitAll(comms.data(), (int)devlist.size(), devlist.data());
+        if (r != ncclSuccess) {
+            std::string m = std::string("ncclCommInitAll: ") + nccl().GetErrorString(r);
+            closyr_ctx_destroy(ctx);
+            return fail(nullptr, CLOSYR_E_CUDA, m);
+        }
+        for (size_t i = 0; i < ctx->devs.size(); i++) ctx->devs[i].comm = comms[i];
+    }
+    if (ctx->devs.size() > 1) {
+        for (size_t i = 1; i < ctx->devs.size(); i++) {       // closyr_rank_resident gathers the scores on device 0
             cudaSetDevice(ctx->devs[0].device);
             int can = 0;
             cudaDeviceCanAccessPeer(&can, ctx->devs[0].device, ctx->devs[i].device);
@@ -339,6 +407,7 @@ void closyr_ctx_destroy(closyr_ctx *ctx)
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.comm) nccl().CommDestroy(d.comm);
         for (DevBuf *b : { &d.xs, &d.ys, &d.leaf_tab, &d.scores, &d.rflags, &d.partials, &d.partials_all, &d.flush, &d.eval_xs,
                            &d.eval_f, &d.eval_status, &d.rank_a, &d.rank_b })
             b->release();
@@ -441,7 +510,7 @@ int closyr_score_resident(closyr_ctx *ctx, int32_t max_leafs, float *device_ms)
     if (ctx->n_expr < 0) return fail(ctx, CLOSYR_E_STATE, "no resident population");
     const int D = (int)ctx->devs.size();
     const int64_t nch = n_chunks_of(ctx->n_points);
-    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && D > 1;
+    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && (D > 1 || ctx->n_ranks > 1);
     for (auto &d : ctx->devs) {
         CU(ctx, cudaSetDevice(d.device));
         CU(ctx, cudaEventRecord(d.ev0, d.stream));
@@ -453,52 +522,59 @@ int closyr_score_resident(closyr_ctx *ctx, int32_t max_leafs, float *device_ms)
             if (rc) return rc;
         }
     } else {
-        // aligned power-of-two chunk span per device; device 0 gathers one partial triple per expression
-        const int64_t span = pow2_ceil((nch + D - 1) / D);
-        DeviceState &d0 = ctx->devs[0];
+        // Point sharding: part q of P evaluates all expressions on an aligned power-of-two span of chunks and leaves one
+        // (sum, max, non-real) triple per expression in row q of the [P][n_expr][3] table; ONE in-place NCCL all-gather
+        // completes the table on every device; every device then combines the rows with the fixed tree for its share
+        // of the expressions (in one process: a slice each; across processes: all of them, every rank returns all scores).
+        const int P = D > 1 ? D : ctx->n_ranks;
+        const int64_t span = pow2_ceil((nch + P - 1) / P);
         const int64_t ne = ctx->n_expr;
-        CU(ctx, cudaSetDevice(d0.device));
-        CU(ctx, d0.partials_all.reserve((size_t)D * std::max<int64_t>(1, ne) * 3 * 8));
         int parts = 0;
+        for (int q = 0; q < P; q++)
+            if (std::min(nch, (int64_t)q * span) < std::min(nch, (int64_t)q * span + span)) parts = q + 1;
         for (int i = 0; i < D; i++) {
             DeviceState &d = ctx->devs[(size_t)i];
-            const int64_t lo = std::min(nch, (int64_t)i * span), hi = std::min(nch, lo + span);
+            const int q = D > 1 ? i : ctx->rank;
+            const int64_t lo = std::min(nch, (int64_t)q * span), hi = std::min(nch, lo + span);
             d.chunk_lo = lo;
             d.chunk_hi = hi;
-            if (hi <= lo) continue;
-            parts = i + 1;
+            d.fin_lo = D > 1 ? ne * i / D : 0;
+            d.fin_hi = D > 1 ? ne * (i + 1) / D : ne;
             CU(ctx, cudaSetDevice(d.device));
-            double *dst = nullptr;
-            if (i == 0) dst = (double *)d0.partials_all.p;
-            else {
-                CU(ctx, d.partials_all.reserve((size_t)std::max<int64_t>(1, ne) * 3 * 8));
-                dst = (double *)d.partials_all.p;
-            }
-            int rc = launch_range(ctx, d, max_leafs, lo, hi, false, dst);
-            if (rc) return rc;
-            CU(ctx, cudaEventRecord(d.done, d.stream));
-        }
-        CU(ctx, cudaSetDevice(d0.device));
-        for (int i = 1; i < parts; i++) {
-            DeviceState &d = ctx->devs[(size_t)i];
-            CU(ctx, cudaStreamWaitEvent(d0.stream, d.done, 0));
-            CU(ctx, cudaMemcpyPeerAsync((double *)d0.partials_all.p + (size_t)i * ne * 3, d0.device, d.partials_all.p,
-                                        d.device, (size_t)ne * 3 * 8, d0.stream));
+            CU(ctx, d.partials_all.reserve((size_t)P * std::max<int64_t>(1, ne) * 3 * 8));
+            double *mine = (double *)d.partials_all.p + (size_t)q * ne * 3;
+            if (hi > lo) {
+                int rc = launch_range(ctx, d, max_leafs, lo, hi, false, mine);
+                if (rc) return rc;
+            } else if (ne > 0) CU(ctx, cudaMemsetAsync(mine, 0, (size_t)ne * 3 * 8, d.stream));
         }
         if (ne > 0) {
-            FinalizeParams fp;
-            fp.meta = (const uint32_t *)d0.pop.meta.p;
-            fp.partials = (const double *)d0.partials_all.p;
-            fp.n_expr = ne;
-            fp.n_tiles_total = std::max(1, parts);
-            fp.max_leafs = max_leafs;
-            fp.n = ctx->n_points;
-            fp.scores = (double *)d0.scores.p;
-            fp.rflags = (uint8_t *)d0.rflags.p;
-            fp.out_partials = nullptr;
-            launch_finalize(fp, d0.stream);
-            ctx->launches++;
-            CU(ctx, cudaGetLastError());
+            NC(ctx, nccl().GroupStart());
+            for (int i = 0; i < D; i++) {
+                DeviceState &d = ctx->devs[(size_t)i];
+                const int q = D > 1 ? i : ctx->rank;
+                NC(ctx, nccl().AllGather((const double *)d.partials_all.p + (size_t)q * ne * 3, d.partials_all.p, (size_t)ne * 3, ncclDouble, d.comm, d.stream));
+            }
+            NC(ctx, nccl().GroupEnd());
+            for (int i = 0; i < D; i++) {
+                DeviceState &d = ctx->devs[(size_t)i];
+                if (d.fin_hi <= d.fin_lo) continue;
+                CU(ctx, cudaSetDevice(d.device));
+                FinalizeParams fp;
+                fp.meta = (const uint32_t *)d.pop.meta.p + d.fin_lo;
+                fp.partials = (const double *)d.partials_all.p + (size_t)d.fin_lo * 3;
+                fp.part_stride = ne;
+                fp.n_expr = d.fin_hi - d.fin_lo;
+                fp.n_tiles_total = std::max(1, parts);
+                fp.max_leafs = max_leafs;
+                fp.n = ctx->n_points;
+                fp.scores = (double *)d.scores.p + d.fin_lo;
+                fp.rflags = (uint8_t *)d.rflags.p + d.fin_lo;
+                fp.out_partials = nullptr;
+                launch_finalize(fp, d.stream);
+                ctx->launches++;
+                CU(ctx, cudaGetLastError());
+            }
         }
     }
     for (auto &d : ctx->devs) {
@@ -518,21 +594,53 @@ int closyr_score_resident(closyr_ctx *ctx, int32_t max_leafs, float *device_ms)
     return CLOSYR_OK;
 }
 
+int closyr_comm_unique_id(uint8_t *out_id)
+{
+    if (!out_id) return fail(nullptr, CLOSYR_E_ARG, "bad arguments to closyr_comm_unique_id");
+    if (!nccl().ok) return fail(nullptr, CLOSYR_E_CUDA, "NCCL (libnccl.so.2) not found");
+    static_assert(sizeof(ncclUniqueId) == CLOSYR_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, CLOSYR_E_CUDA, std::string("ncclGetUniqueId: ") + nccl().GetErrorString(r));
+    memcpy(out_id, &id, sizeof(id));
+    return CLOSYR_OK;
+}
+
+int closyr_comm_init_rank(closyr_ctx *ctx, int n_ranks, int rank, const uint8_t *id_bytes)
+{
+    if (!ctx || !id_bytes || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_comm_init_rank");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err.clear();
+    if (ctx->devs.size() != 1 || !(ctx->flags & CLOSYR_SHARD_POINTS))
+        return fail(ctx, CLOSYR_E_STATE, "closyr_comm_init_rank: a context with ONE device created with CLOSYR_SHARD_POINTS");
+    if (!nccl().ok) return fail(ctx, CLOSYR_E_CUDA, "NCCL (libnccl.so.2) not found");
+    DeviceState &d = ctx->devs[0];
+    if (d.comm) return fail(ctx, CLOSYR_E_STATE, "closyr_comm_init_rank: already initialised");
+    CU(ctx, cudaSetDevice(d.device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    NC(ctx, nccl().CommInitRank(&d.comm, n_ranks, id, rank));
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return CLOSYR_OK;
+}
+
 int closyr_download_scores(closyr_ctx *ctx, double *out_scores, uint8_t *out_flags)
 {
     if (!ctx || !out_scores) return fail(ctx, CLOSYR_E_ARG, "bad arguments to closyr_download_scores");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->err.clear();
     if (!ctx->scored) return fail(ctx, CLOSYR_E_STATE, "no scores: call closyr_score_resident first");
-    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && ctx->devs.size() > 1;
+    const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && (ctx->devs.size() > 1 || ctx->n_ranks > 1);
     for (size_t i = 0; i < ctx->devs.size(); i++) {
         DeviceState &d = ctx->devs[i];
-        if (by_points && i > 0) break;
-        const int64_t ne = d.pop.hi - d.pop.lo;
+        // what this device returns: its block of the population, or (point sharding) the slice it finalised
+        const int64_t lo = by_points ? d.fin_lo : d.pop.lo, off = by_points ? d.fin_lo : 0;
+        const int64_t ne = by_points ? d.fin_hi - d.fin_lo : d.pop.hi - d.pop.lo;
         if (ne <= 0) continue;
         CU(ctx, cudaSetDevice(d.device));
-        CU(ctx, cudaMemcpyAsync(out_scores + d.pop.lo, d.scores.p, (size_t)ne * 8, cudaMemcpyDeviceToHost, d.stream));
-        if (out_flags) CU(ctx, cudaMemcpyAsync(out_flags + d.pop.lo, d.rflags.p, (size_t)ne, cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaMemcpyAsync(out_scores + lo, (const double *)d.scores.p + off, (size_t)ne * 8, cudaMemcpyDeviceToHost, d.stream));
+        if (out_flags) CU(ctx, cudaMemcpyAsync(out_flags + lo, (const uint8_t *)d.rflags.p + off, (size_t)ne, cudaMemcpyDeviceToHost, d.stream));
     }
     for (auto &d : ctx->devs) {
         CU(ctx, cudaSetDevice(d.device));
@@ -626,6 +734,7 @@ int closyr_finalize_partials(closyr_ctx *ctx, const void *dev_partials_all, int 
         FinalizeParams fp;
         fp.meta = (const uint32_t *)d.pop.meta.p;
         fp.partials = (const double *)dev_partials_all;
+        fp.part_stride = ctx->n_expr;
         fp.n_expr = ctx->n_expr;
         fp.n_tiles_total = n_parts;
         fp.max_leafs = max_leafs;
@@ -676,17 +785,22 @@ int closyr_rank_resident(closyr_ctx *ctx, int64_t k, int64_t *out_indices)
     CU(ctx, cudaSetDevice(d0.device));
     const bool by_points = (ctx->flags & CLOSYR_SHARD_POINTS) && ctx->devs.size() > 1;
     const double *scores = (const double *)d0.scores.p;
-    if (ctx->devs.size() > 1 && !by_points) {
-        // gather every shard's scores on device 0 (peer copy over NVLink when available)
-        CU(ctx, d0.rank_b.reserve((size_t)ne * 8 + (size_t)k * 8));
+    CU(ctx, d0.rank_b.reserve((size_t)ne * 8 + (size_t)k * 8));
+    if (ctx->devs.size() > 1) {
+        // gather every device's scores on device 0 (peer copy over NVLink when available)
         for (auto &d : ctx->devs) {
-            const int64_t n_here = d.pop.hi - d.pop.lo;
+            const int64_t lo = by_points ? d.fin_lo : d.pop.lo, off = by_points ? d.fin_lo : 0;
+            const int64_t n_here = by_points ? d.fin_hi - d.fin_lo : d.pop.hi - d.pop.lo;
             if (n_here <= 0) continue;
-            CU(ctx, cudaMemcpyPeerAsync((double *)d0.rank_b.p + d.pop.lo, d0.device, d.scores.p, d.device,
+            CU(ctx, cudaSetDevice(d.device));
+            CU(ctx, cudaEventRecord(d.done, d.stream));
+            CU(ctx, cudaSetDevice(d0.device));
+            CU(ctx, cudaStreamWaitEvent(d0.stream, d.done, 0));
+            CU(ctx, cudaMemcpyPeerAsync((double *)d0.rank_b.p + lo, d0.device, (const double *)d.scores.p + off, d.device,
                                         (size_t)n_here * 8, d0.stream));
         }
         scores = (const double *)d0.rank_b.p;
-    } else CU(ctx, d0.rank_b.reserve((size_t)ne * 8 + (size_t)k * 8));
+    }
     CU(ctx, d0.rank_a.reserve(rank_scratch_bytes(ne)));
     int64_t *d_out = (int64_t *)((double *)d0.rank_b.p + ne);
     ctx->launches += launch_rank(scores, ne, k, d0.rank_a.p, d_out, d0.stream);

@@ -510,7 +510,7 @@ __global__ void finalize_kernel(const FinalizeParams p)
     double mx = 0.0, nonreal = 0.0;
     bool used_full = false;
     for (int t = 0; t < p.n_tiles_total; t++) {
-        const double *in = p.partials + ((int64_t)t * p.n_expr + e) * 3;
+        const double *in = p.partials + ((int64_t)t * p.part_stride + e) * 3;
         double s = in[0];
         mx = fmax(mx, in[1]);
         const double nr = floor(in[2]);

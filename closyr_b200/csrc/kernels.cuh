@@ -71,7 +71,8 @@ void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab,
 
 struct FinalizeParams {
     const uint32_t *meta;
-    const double *partials;           // [n_tiles_total][n_expr][3]
+    const double *partials;           // [n_tiles_total][part_stride][3], first expression of this launch at column 0
+    int64_t part_stride;              // expressions per row of `partials` (>= n_expr: a launch may combine a slice)
     int64_t n_expr;
     int32_t n_tiles_total;
     int32_t max_leafs;

@@ -106,9 +106,14 @@ def combine_partials_reference(parts):
 
 
 def score_point_sharded(ctx, max_leafs, n_points, rank, world, dist, torch_device):
-    """Point-sharded scoring of the resident population of `ctx` (every rank holds the whole population):
-    partials of this rank's chunk span -> NCCL all-gather -> fixed-tree combine + score epilogue on device.
+    """Point-sharded scoring of the resident population of `ctx` (every rank holds the whole population).
+    world > 1: `ctx` was created with shard=SHARD_POINTS and joined with Context.init_point_sharding; the
+    library computes this rank's partials, all-gathers them with NCCL and combines them (collective call).
+    world == 1 (tests): the same building blocks on one device, partials -> fixed-tree combine.
     Returns (scores, flags) on every rank."""
+    if world > 1:
+        ctx.score_resident(max_leafs)
+        return ctx.download_scores()
     import torch
 
     plan = plan_point_shards(n_points, world)
@@ -117,12 +122,6 @@ def score_point_sharded(ctx, max_leafs, n_points, rank, world, dist, torch_devic
     lo, hi = plan[rank]
     torch.cuda.synchronize(torch_device)        # the library launches on its own (non-blocking) stream
     ctx.score_partials(max_leafs, lo, hi, mine.data_ptr())
-    parts = sum(1 for a, b in plan if b > a)
-    allp = torch.empty(world * ne * 3, dtype=torch.float64, device=torch_device)
-    if world > 1:
-        dist.all_gather_into_tensor(allp, mine)
-    else:
-        allp.copy_(mine)
     torch.cuda.synchronize(torch_device)
-    ctx.finalize_partials(allp.data_ptr(), max(1, parts), max_leafs)
+    ctx.finalize_partials(mine.data_ptr(), 1, max_leafs)
     return ctx.download_scores()

@@ -187,7 +187,23 @@ int closyr_score_from_values(closyr_ctx *ctx, const double *f_of_xs, const doubl
  */
 int closyr_rank_resident(closyr_ctx *ctx, int64_t k, int64_t *out_indices);
 
-/* point-sharded building blocks (used by one-process-per-GPU launchers, see closyr_b200/sharder.py):
+/*
+ * Point sharding (CLOSYR_SHARD_POINTS): the points are split into aligned power-of-two spans of 128-point chunks, one
+ * per GPU; every GPU evaluates all expressions on its span, the per-expression partial (sum, max, non-real count)
+ * triples are exchanged with ONE NCCL all-gather over NVLink issued by this library on its own streams, and combined by
+ * the same fixed binary tree, so a score is bit-identical for 1, 2, 4 or 8 GPUs.  With several devices in one context
+ * (one process driving the box: the JVM's shape) closyr_ctx_create builds the communicators itself and
+ * closyr_score_resident / closyr_score_batch do everything.  With one process per GPU each process creates a context
+ * with ONE device and CLOSYR_SHARD_POINTS, rank 0 calls closyr_comm_unique_id, the caller hands the 128 bytes to every
+ * rank (any transport), every rank calls closyr_comm_init_rank, and from then on closyr_score_resident is collective:
+ * every rank calls it with the same resident population and returns ALL scores.
+ * Replaces the pmap over the population for very large point counts (src/closyr/ga.clj:58-88).
+ */
+#define CLOSYR_COMM_ID_BYTES 128
+int closyr_comm_unique_id(uint8_t *out_id /* CLOSYR_COMM_ID_BYTES */);
+int closyr_comm_init_rank(closyr_ctx *ctx, int n_ranks, int rank, const uint8_t *id /* CLOSYR_COMM_ID_BYTES */);
+
+/* point-sharded building blocks for callers that bring their own exchange (closyr_b200/sharder.py emulates ranks with them):
  * partials[3*n_expr] = {sum, max, nonreal_count} of this device's point range, combined afterwards. */
 int closyr_score_partials_resident(closyr_ctx *ctx, int32_t max_leafs, int64_t chunk_begin, int64_t chunk_end,
                                    void *dev_partials /* device pointer, 3*n_expr doubles */);

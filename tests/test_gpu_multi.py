@@ -80,3 +80,20 @@ def test_in_process_multi_device_context(shard):
         order = many.rank(50)
     assert got.tolist() == want.tolist()
     assert order.tolist() == np.argsort(want, kind="stable")[::-1][:50].tolist()
+
+
+def test_multi_process_point_sharding():
+    """One process per GPU (torchrun): the NCCL all-gather of the partial sums is the library's own."""
+    import os
+    import subprocess
+    import sys
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_point_shard_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", worker],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MP_POINT_SHARD OK" in out.stdout
