@@ -42,3 +42,27 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run(["--steps", "1", "--warmup", "0", "--workload", "c2", "--no-cpu-baseline"], timeout=300)
     assert r.returncode != 0
     assert r.stdout.strip() == ""            # no JSON line, no silent CPU path
+
+
+def test_reference_arm_loads_nothing_of_the_product():
+    """The reference arm's process maps oracle/ only: no closyr_b200 module, no libclosyr_b200.so."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'c2', '--steps', '1', '--warmup', '0']\n"
+            "runpy.run_path('bench.py', run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libclosyr_b200' not in maps, 'the product library is mapped'\n"
+            "assert 'liboracle' in maps\n"
+            "assert not any(m == 'closyr_b200' or m.startswith('closyr_b200.') for m in sys.modules), 'closyr_b200 imported'\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_both_arms_describe_the_same_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.config_of("c3", "population")
+    assert a["population"] == 100000 and a["points"] == 4096 and a["max_leafs"] == 40
+    assert list(a) == ["workload", "population", "points", "max_leafs", "sharding", "generator_seed", "l2", "step"]
+    # the committed cache of the default workload holds the whole population, so the reference arm needs no generator
+    texts, source = bench.population_texts("c3", 100000)
+    assert len(texts) == 100000 and source.startswith("committed cache")
