@@ -50,19 +50,40 @@ def assert_scores_close(got, want, texts=None):
     assert err[i] <= REL_TOL, "expr %d %s: gpu %r oracle %r" % (i, texts[i] if texts else "", got[i], want[i])
 
 
-def assert_population_scores_match(texts, xs, ys, max_leafs, got, min_stable=0.5):
-    """1e-9 relative wherever the oracle's own score is stable under +-1 ulp perturbations of its math
-    library (`ok`); a deviation anywhere else must be reproducible by such a perturbation (knife edges:
-    domain boundaries, branch cuts, chaotic arguments such as Cos(E^(x^2)))."""
-    want, ok = O.score_batch_conditioned(texts, xs, ys, max_leafs)
-    assert ok.mean() >= min_stable
+PARITY_REPORT = []      # one record per population checked (printed at the end of the session with `pytest -s`)
+
+
+def assert_population_scores_match(texts, xs, ys, max_leafs, got, probes=8, explain_limit=400):
+    """The bar: 1e-9 relative on every score that fp64 arithmetic determines.
+      * `ok` = the oracle's own score is stable when every result of its math library moves by +-1 ulp;
+      * a deviation above 1e-9 on a STABLE expression that such a perturbation (2 ulp: the documented bound of the CUDA
+        routines) cannot reproduce is a real discrepancy: none is allowed;
+      * a deviation anywhere else must be reproducible the same way (knife edges: a point on a domain boundary or a
+        branch cut, chaotic arguments such as Cos(E^(x^2))): no unexplained deviation is allowed there either;
+      * explained deviations among the stable expressions are capped at 0.5 % of the population.
+    The stable fraction is what it is (reported, not a gate): on a transcendental-heavy population on extreme points
+    most expressions are chaotic, and the bar for those is "explained"."""
+    want, ok = O.score_batch_conditioned(texts, xs, ys, max_leafs, probes=probes)
     err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
     bad = np.nonzero(err > REL_TOL)[0]
-    for i in bad:
-        assert O.score_discrepancy_explained(texts[i], xs, ys, max_leafs, got[i], want[i]), \
-            "expr %d %s: gpu %r oracle %r" % (i, texts[i], got[i], want[i])
-    assert (ok[bad]).sum() <= 0.02 * len(texts), "too many knife-edge cases among the stable expressions"
+    check = bad if len(bad) <= explain_limit else np.random.default_rng(0).choice(bad, explain_limit, replace=False)
+    unexplained = [int(i) for i in check
+                   if not O.score_discrepancy_explained(texts[i], xs, ys, max_leafs, got[i], want[i])]
+    rec = {"expressions": len(texts), "points": len(xs), "stable_fraction": float(ok.mean()),
+           "within_1e-9": float((err <= REL_TOL).mean()), "deviating": int(len(bad)), "deviating_stable": int(ok[bad].sum()),
+           "explain_checked": int(len(check)), "unexplained": len(unexplained),
+           "max_rel_err_stable": float(err[ok].max()) if ok.any() else None}
+    PARITY_REPORT.append(rec)
+    assert not unexplained, "unexplained deviations, first: expr %d %s: gpu %r oracle %r" % (
+        unexplained[0], texts[unexplained[0]], got[unexplained[0]], want[unexplained[0]])
+    assert ok[bad].sum() <= max(2, 0.005 * len(texts)), "too many knife-edge cases among the stable expressions: %r" % rec
     return want, ok
+
+
+def test_zz_parity_report():
+    """Prints what the population checks of this session saw (pytest -s)."""
+    for rec in PARITY_REPORT:
+        print("PARITY", rec)
 
 
 # ------------------------------------------------------------------ the reference's own known-answer tests
@@ -408,7 +429,7 @@ def test_golden_corpus_with_crossovers_and_mutations(ctx, points):
     texts = golden_corpus_population()
     assert len(texts) > 700
     got, flags = gpu_scores(ctx, texts, xs, ys, 40)
-    want, ok = assert_population_scores_match(texts, xs, ys, 40, got, min_stable=0.4)
+    want, ok = assert_population_scores_match(texts, xs, ys, 40, got)
     assert ((flags & L.R_TOO_BIG) != 0).tolist() == [O.leaf_count(t) > 40 for t in texts]
     stable = np.nonzero(ok)[0]
     assert int(stable[np.argmax(got[stable])]) == int(stable[np.argmax(want[stable])])     # same best expression
@@ -426,4 +447,25 @@ def test_generated_expressions_on_extreme_points(ctx, seed, mix):
     check_eval_against_oracle(texts, xs, f, status)
     ys = np.linspace(-2.0, 2.0, len(xs))
     got, _ = gpu_scores(ctx, texts, xs, ys, 40)
-    assert_population_scores_match(texts, xs, ys, 40, got, min_stable=0.3)
+    assert_population_scores_match(texts, xs, ys, 40, got)
+
+
+def test_whole_configs2_population_against_the_oracle(ctx):
+    """BASELINE.json configs[2] at full size: every one of the 100K expressions x 4096 points against the oracle
+    (the bench only spot-checks the first 2000)."""
+    import bench
+    pop_n, n_points, max_leafs, mix, _ = bench.WORKLOADS["c3"]
+    xs, ys = bench.synth_points(n_points)
+    b = cb.PopulationBuilder()
+    texts = b.generate(bench.SEED, pop_n, max_leafs, mix, want_texts=True)
+    ctx.set_points(xs, ys)
+    got, flags = ctx.score_batch(b.view(), max_leafs)
+    want, ok = assert_population_scores_match(texts, xs, ys, max_leafs, got, probes=3, explain_limit=300)
+    # what the GA does with the scores: the same best expression, the same outcome of compete's `>=` on neighbours
+    # (src/closyr/ga.clj:43) wherever both scores are determined by fp64
+    stable = np.nonzero(ok)[0]
+    assert int(stable[np.argmax(got[stable])]) == int(stable[np.argmax(want[stable])])
+    a, c = np.arange(0, pop_n - 1, 2), np.arange(1, pop_n, 2)
+    both = ok[a] & ok[c]
+    assert ((got[a] >= got[c]) == (want[a] >= want[c]))[both].all()
+    assert ((got == O.MIN_SCORE) == (want == O.MIN_SCORE)).all()
