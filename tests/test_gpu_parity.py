@@ -80,12 +80,6 @@ def assert_population_scores_match(texts, xs, ys, max_leafs, got, probes=8, expl
     return want, ok
 
 
-def test_zz_parity_report():
-    """Prints what the population checks of this session saw (pytest -s)."""
-    for rec in PARITY_REPORT:
-        print("PARITY", rec)
-
-
 # ------------------------------------------------------------------ the reference's own known-answer tests
 def run_args(ctx, xs, ys):
     return ops.to_run_args(xs, ys, ctx=ctx)
@@ -469,3 +463,9 @@ def test_whole_configs2_population_against_the_oracle(ctx):
     both = ok[a] & ok[c]
     assert ((got[a] >= got[c]) == (want[a] >= want[c]))[both].all()
     assert ((got == O.MIN_SCORE) == (want == O.MIN_SCORE)).all()
+
+
+def test_zz_parity_report():
+    """Prints what the population checks of this session saw (pytest -s)."""
+    for rec in PARITY_REPORT:
+        print("PARITY", rec)
