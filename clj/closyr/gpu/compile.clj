@@ -60,7 +60,7 @@
       (and (some? (leaf-value e)) (not (.equals e x))) :const
       :else :general)))
 
-(declare need)
+(declare need unary-ops)
 
 (defn- need-nary [^IAST n ^ISymbol x]
   (let [k (.argSize n)
@@ -85,7 +85,8 @@
                      :exp (need (.arg2 ^IAST e) x)
                      :general (max (need (.arg1 ^IAST e) x) (inc (need (.arg2 ^IAST e) x)))
                      (need (.arg1 ^IAST e) x)))
-    (and (.isAST e) (= 1 (.argSize ^IAST e))) (need (.arg1 ^IAST e) x)
+    ;; only the heads `gen!` compiles: an unknown head is one LDSPEC and needs nothing (compiler.cpp need())
+    (and (.isAST e) (= 1 (.argSize ^IAST e)) (unary-ops (str (.head ^IAST e)))) (need (.arg1 ^IAST e) x)
     :else 0))
 
 (defn- emitter []

@@ -658,11 +658,12 @@ NodeP crossover(int max_leafs, const Node &e1, const Node &e2, JavaRandom &rng, 
     case 4: n = sub2(std::move(p1), std::move(p2)); break;
     default: n = sub2(std::move(p2), std::move(p1)); break;
     }
-    const bool invalid = t_div_by_zero || leaf_count(*n) > max_leafs;
-    if (invalid || same_expr(*n, e1)) {
-        if (changed) *changed = false;
-        return clone(e1);
-    }
+    if (changed) *changed = false;
+    // "Infinite expression 1/0 encountered.": ops-modify/crossover catches the exception and returns nil, and
+    // ops/crossover-fn falls back to a mutation of e1 (modify.clj:187-189, ops.clj:175-188)
+    if (t_div_by_zero) return nullptr;
+    // too big, or nothing changed: the last operation is kept, e1 comes back as it was (modify.clj:176-180)
+    if (leaf_count(*n) > max_leafs || same_expr(*n, e1)) return clone(e1);
     if (changed) *changed = true;
     return valid_or_default(std::move(n));
 }
@@ -799,6 +800,7 @@ int closyr_crossover_expr(const char *text1, const char *text2, int32_t max_leaf
     if (!a || !b) { set_error("parse error: " + err); return CLOSYR_E_PARSE; }
     JavaRandom r(seed);
     NodeP c = crossover(max_leafs, *a, *b, r, nullptr);
+    if (!c) c = clone(*a);                     // ops-modify/crossover returns nil (the caller mutates instead): e1 as it was
     *out = dup_string(to_fullform(*c));
     return *out ? CLOSYR_OK : CLOSYR_E_NOMEM;
 }
@@ -903,9 +905,13 @@ int closyr_ga_evolve(closyr_ga *g, closyr_ga_stats *st)
         if (e1.score >= e2.score) {
             closyr_ga::Pheno child;
             bool changed = false;
-            if (!use_mutation) child.expr = crossover(g->max_leafs, *e1.expr, *e2.expr, rng, &changed);   // ops.clj:175-188
-            else child.expr = mutate(g->max_leafs, *e1.expr, rng, nullptr);
-            kind[(size_t)k] = use_mutation ? 1 : 2;
+            bool crossed = false;
+            if (!use_mutation) {
+                child.expr = crossover(g->max_leafs, *e1.expr, *e2.expr, rng, &changed);     // ops.clj:175-188
+                crossed = child.expr != nullptr;
+            }
+            if (!child.expr) child.expr = mutate(g->max_leafs, *e1.expr, rng, nullptr);      // also the fallback of a crossover that threw
+            kind[(size_t)k] = crossed ? 2 : 1;
             next[(size_t)(2 * k + 1)] = std::move(child);
         } else next[(size_t)(2 * k + 1)] = std::move(e2);
         next[(size_t)(2 * k)] = std::move(e1);
