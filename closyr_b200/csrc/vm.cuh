@@ -800,11 +800,7 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         const uint32_t pre_ = mask_nan<P>(acc);                                                     \
         body_;                                                                                      \
         dx |= mask_nan<P>(acc) & ~pre_;                                                             \
-        if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) {                                     \
-            res.ev = (ev | dx) & valid;                                                             \
-            res.mx = chunk_residuals(acc, yp, valid, sum_addr);                                     \
-            return res;                                                                             \
-        }                                                                                           \
+        if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) goto finish;                          \
     }
 #pragma unroll 1
     for (;;) {
@@ -826,7 +822,8 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
         const double c = __hiloint2double((int)chi, (int)clo);
     redo:
         switch (h) {
-        case TH_END: {
+        case TH_END:
+        finish: {
             res.ev = (ev | (dx & mask_nan<P>(acc))) & valid;
             res.mx = chunk_residuals(acc, yp, valid, sum_addr);     // overwritten by the slow path when a point was reported
             return res;
@@ -838,11 +835,7 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
             CLOSYR_PUSH_IF()
             ldg_x(reinterpret_cast<const double *>(reinterpret_cast<const char *>(tab) + __double_as_longlong(c)), acc);
             dx |= mask_nan<P>(acc);                          // x is a number: a NaN entry is a domain exit
-            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) {
-                res.ev = (ev | dx) & valid;
-                res.mx = chunk_residuals(acc, yp, valid, sum_addr);
-                return res;
-            }
+            if (__all_sync(0xffffffffu, every_point_nan<P>(acc))) goto finish;
             break;
         }
         case TH_MOD:                                         // PUSH / SRCX modifiers of a function that has no table
