@@ -184,7 +184,7 @@ def population_texts(workload, count):
     return texts, "generated by a child process (scripts/dump_population.py)"
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """The reference arm: the CPU restatement of closyr's scoring path (oracle/oracle.c) on every host core, the
     WHOLE population of the workload per step (a bounded sample only where a step would not fit the run).
     The real reference (Clojure + Symja on a JVM) cannot run in this image: no JVM, no jars, no network.
@@ -223,7 +223,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "expr-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -279,13 +279,23 @@ def main():
     ap.add_argument("--population", type=int, default=0, help="override the workload's population (configs[4] sweep)")
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (configs[4] sweep)")
     args = ap.parse_args()
+    # ONE JSON line on stdout: native libraries print there too (NCCL announces its version when NCCL_DEBUG is set), so
+    # file descriptor 1 points at stderr while the run lasts and the line goes to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.population or args.points:
         p0, n0, ml, mx, d0 = WORKLOADS[args.workload]
         p1, n1 = args.population or p0, args.points or n0
         WORKLOADS[args.workload] = (p1, n1, ml, mx, "configs[4] sweep point (%s shape): pop %d x %d points, max-leafs %d"
                                     % (args.workload, p1, n1, ml))
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch
@@ -475,7 +485,7 @@ def main():
         line["c4_8gpu"] = c4
 
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
