@@ -426,8 +426,16 @@ def main():
             roof["hbm_peak_GBps_measured"] = peaks.get("hbm_gbs")
         except Exception:
             pass
+        # the host GA's next step on the scores: the best 100 expressions, ranked on the device (row N1)
+        rank_ms = None
+        if want_clocks:
+            ctx.rank(100)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.rank(100)
+            rank_ms = 1e3 * (time.perf_counter() - t0) / 3
         out = {
-            "ms_per_step": ms_per_step, "value": value,
+            "ms_per_step": ms_per_step, "value": value, "rank_top100_ms": rank_ms,
             "e2e": {"value": pop_n * n_points / e2e_s, "unit": "expr-points/s", "h2d_bytes_per_step": bytes_in,
                     "d2h_bytes_per_step": bytes_out, "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
@@ -469,6 +477,7 @@ def main():
         "ms_per_generation": m["ms_per_step"],
         "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "clocks": m["clocks"],
         "wall_ms_per_step_incl_flush": m["wall_ms_per_step_incl_flush"],
+        "rank_top100_ms": m["rank_top100_ms"],
     }
     if rank == 0 and not args.no_cpu_baseline:
         line.update(cpu_side(args.workload, m, 2000, args.cpu_sample))

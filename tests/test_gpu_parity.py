@@ -465,6 +465,26 @@ def test_whole_configs2_population_against_the_oracle(ctx):
     assert ((got == O.MIN_SCORE) == (want == O.MIN_SCORE)).all()
 
 
+def test_ranking_a_million_scores_with_ties(ctx):
+    """closyr_rank_resident at the size of configs[3] (2^20 + 1 expressions, so the network pads to 2^21): the tiled
+    bitonic passes (shared memory) and the cross-tile steps give the host's order, ties in descending index."""
+    kinds = ["x", "Plus(1,x)", "Times(2,x)", "Sin(x)", "Plus(x,Cos(x))", "Power(x,2)", "Log(x)", "Power(x,-1)",
+             "Indeterminate", "Plus(Rational(1,2),x)", "Power(E,x)", "Times(x,x,x)"]
+    n = (1 << 20) + 1
+    texts = [kinds[(i * 7 + i // 13) % len(kinds)] for i in range(n)]
+    xs = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0])
+    ys = np.array([1.0, 2.0, 30.0, 4.0, 5.0, 6.0, 10.0])
+    b = cb.PopulationBuilder()
+    b.add_many(texts)
+    ctx.set_points(xs, ys)
+    scores, _ = ctx.score_batch(b.view(), 40)
+    order = ctx.rank()
+    want = np.argsort(scores, kind="stable")[::-1]
+    assert order.tolist() == want.tolist()
+    top = ctx.rank(100)
+    assert top.tolist() == want[:100].tolist()
+
+
 def test_zz_parity_report():
     """Prints what the population checks of this session saw (pytest -s)."""
     for rec in PARITY_REPORT:
