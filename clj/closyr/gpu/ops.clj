@@ -36,8 +36,11 @@
   (first (score-batch run-args run-config [pheno])))
 
 (defn with-scores
-  "Two-phase replacement of ga/with-score (src/closyr/ga.clj:25-29) for a whole population."
+  "Two-phase replacement of ga/with-score (src/closyr/ga.clj:25-29) for a whole population: one device call for
+   every phenotype that has no :score yet.  Matched by POSITION, so nothing depends on how mutation-fn / crossover-fn
+   hand out :id values."
   [run-args run-config pop]
-  (let [todo (filterv (complement :score) pop)
-        scores (zipmap (map :id todo) (score-batch run-args run-config todo))]
-    (mapv (fn [p] (if (:score p) p (assoc p :score (scores (:id p))))) pop)))
+  (let [pop    (vec pop)
+        idx    (vec (keep-indexed (fn [i p] (when-not (:score p) i)) pop))
+        scores (if (seq idx) (score-batch run-args run-config (mapv pop idx)) [])]
+    (reduce (fn [acc [i s]] (assoc-in acc [i :score] s)) pop (map vector idx scores))))
