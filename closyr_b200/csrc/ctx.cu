@@ -28,7 +28,7 @@ int launch_rank(const double *scores, int64_t n, int64_t k, void *scratch, int64
 void *pinned_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
