@@ -109,3 +109,31 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "ctx_create rc=" in out.stdout
+
+
+def test_comm_entry_points_without_a_gpu():
+    """The NCCL id is plain bytes (no device needed to make one); joining a communicator needs a context, and a context
+    needs a GPU: without one the calls fail with a code, they do not crash."""
+    import ctypes as C
+    lib = L.lib()
+    ident = (C.c_uint8 * L.COMM_ID_BYTES)()
+    rc = lib.closyr_comm_unique_id(ident)
+    assert rc in (0, L.E_CUDA if hasattr(L, "E_CUDA") else -2)
+    assert lib.closyr_comm_unique_id(None) != 0
+    assert lib.closyr_comm_init_rank(None, 2, 0, ident) != 0
+
+
+def test_kernels_use_the_hardware_paths_the_design_names():
+    """SASS of the in-tree library: the threaded code arrives by TMA bulk copy (UBLKCP) against an mbarrier (SYNCS), the
+    interpreters dispatch through branch-target tables (BRX), and nothing uses tensor cores."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(ROOT, "closyr_b200", "libclosyr_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    kernel = sass[sass.index("score_kernel"):]
+    kernel = kernel[:kernel.index("Function :", 10)] if "Function :" in kernel[10:] else kernel
+    assert "UBLKCP" in kernel and "SYNCS" in kernel and "BRX" in kernel
+    assert "HMMA" not in sass and "UTCMMA" not in sass and "DMMA" not in sass
