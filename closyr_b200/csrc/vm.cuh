@@ -709,7 +709,7 @@ __device__ __forceinline__ double chunk_residuals(const double (&v)[4], const do
     OP " %1, %1, " B1 ";\n\t"                \
     OP " %2, %2, " B2 ";\n\t"                \
     OP " %3, %3, " B3 ";\n\t"
-#define CLOSYR_CHEAP_HANDLERS(S, T)                                                            \
+#define CLOSYR_CHEAP_HANDLERS(S, T, OFF)                                                          \
     /* leaf loads: the P forms push acc first and fall through */                             \
     "LDXP_" S ":\n\t" CLOSYR_PUSH_PTX(S)                                                       \
     "LDX_" S ":\n\t"                                                                           \
@@ -757,7 +757,7 @@ __device__ __forceinline__ double chunk_residuals(const double (&v)[4], const do
     CLOSYR_OP4("mul.rn.f64", "s0_", "s1_", "s2_", "s3_") "bra.uni NEXT_" T ";\n\t"             \
     /* dispatch of this copy: start loading the following entry into the other copy's registers, then jump */ \
     "NEXT_" S ":\n\t"                                                                          \
-    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%4+16];\n\t"                  \
+    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%4" OFF "];\n\t"                \
     "add.u32 %4, %4, 16;\n\t"                                                                  \
     "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", TAB_" S ", TABP_" S \
     ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S       \
@@ -812,8 +812,8 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
             ".reg .f64 c_, s0_, s1_, s2_, s3_;\n\t"
             "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%4];\n\t"
             "bra.uni NEXT_A;\n\t"
-            CLOSYR_CHEAP_HANDLERS("A", "B")
-            CLOSYR_CHEAP_HANDLERS("B", "A")
+            CLOSYR_CHEAP_HANDLERS("A", "B", "+16")
+            CLOSYR_CHEAP_HANDLERS("B", "A", "+16")
             "OUT_:\n\t"
             "}\n"
             : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+r"(ip), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
@@ -973,7 +973,9 @@ __device__ __noinline__ Z zrsqrt(Z a) { return zrecip(zsqrt(a)); }
 template <int P> struct CplxArgs { int64_t idx[P]; };
 template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real; };   // left_real: the warp left real mode at some instruction
 
-// The cheap handlers of REAL MODE in PTX, two points per lane (the structure of run_real's block; see there).
+// The cheap handlers of REAL MODE in PTX, two points per lane (the structure of run_real's block; see there), but ONE copy
+// without the prefetch of the next entry: this interpreter's code is cold when a CTA arrives (profiles/
+// r02_design_experiments.md), the second copy cost more instruction-cache lines than the prefetch saved.
 // Operands: %0 %1 the real parts, %2 ip, %3 sm (bit k = slot k holds imaginary parts), %4..%7 = h aux c.lo c.hi of the
 // instruction the block exits on, %8 this lane's slot column, %9 %10 x, %11 %12 this lane's two columns of the tables.
 // A slot operand with imaginary parts, the 1/x table (pole) and everything that is not cheap leave the block.
@@ -993,7 +995,7 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "@p_ bra.uni X_" S ";\n\t"                   \
     "add.u32 t_, aux" S "_, %8;\n\t"             \
     "ld.shared.f64 s0_, [t_];\n\t ld.shared.f64 s1_, [t_+256];\n\t"
-#define CLOSYR_CHEAP2_HANDLERS(S, T)                                                           \
+#define CLOSYR_CHEAP2_HANDLERS(S, T, OFF)                                                         \
     "LDXP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
     "LDX_" S ":\n\t mov.f64 %0, %9;\n\t mov.f64 %1, %10;\n\t bra.uni NEXT_" T ";\n\t"          \
     "LDCP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
@@ -1020,7 +1022,7 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "ADDS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("add.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
     "MULS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("mul.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
     "NEXT_" S ":\n\t"                                                                          \
-    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%2+16];\n\t"                  \
+    "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%2" OFF "];\n\t"                \
     "add.u32 %2, %2, 16;\n\t"                                                                  \
     "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", X_" S ", X_" S \
     ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S      \
@@ -1111,10 +1113,8 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
                 ".reg .b64 ad_, a0_, a1_;\n\t"
                 ".reg .f64 c_, s0_, s1_;\n\t"
                 "mov.b32 z_, 0;\n\t"
-                "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%2];\n\t"
                 "bra.uni NEXT_A;\n\t"
-                CLOSYR_CHEAP2_HANDLERS("A", "B")
-                CLOSYR_CHEAP2_HANDLERS("B", "A")
+                CLOSYR_CHEAP2_HANDLERS("A", "A", "")
                 "OUT_:\n\t"
                 "}\n"
                 : "+d"(a.re[0]), "+d"(a.re[1]), "+r"(ip), "+r"(sm), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
