@@ -95,6 +95,7 @@ struct DevBuf {                       // grow-only device allocation
 struct DevPop {                       // one resident population shard
     DevBuf code, code_off, consts, const_off, meta, aux;
     DevBuf tcode, desc;               // what prepare_kernel derives from the arrays above (threaded code, descriptors)
+    DevBuf key, order;                // grouping keys and the expression order made from them (order_kernel)
     int64_t prepared_stride = -2;     // leaf_stride the threaded code was made for (-1: without tables, -2: not made yet)
     int64_t lo = 0, hi = 0;           // expression range of the caller's population held here
     uint32_t code_base = 0, const_base = 0, max_code = 0, max_consts = 0, n_words = 0;
@@ -112,9 +113,10 @@ struct DevPop {                       // one resident population shard
         v.n_expr = hi - lo;
         v.tcode = (const uint4 *)tcode.p;
         v.desc = (const ExprDesc *)desc.p;
+        v.order = nullptr;            // launch_range decides
         return v;
     }
-    void release() { code.release(); code_off.release(); consts.release(); const_off.release(); meta.release(); aux.release(); tcode.release(); desc.release(); }
+    void release() { code.release(); code_off.release(); consts.release(); const_off.release(); meta.release(); aux.release(); tcode.release(); desc.release(); key.release(); order.release(); }
 };
 
 struct DeviceState {
@@ -232,14 +234,18 @@ int prepare_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, int64_t leaf_stri
     if (dp.prepared_stride == want || dp.hi <= dp.lo) return CLOSYR_OK;
     CU(ctx, dp.tcode.reserve((size_t)dp.n_words * 16 + 16));
     CU(ctx, dp.desc.reserve((size_t)(dp.hi - dp.lo) * sizeof(ExprDesc)));
+    CU(ctx, dp.key.reserve((size_t)(dp.hi - dp.lo) * 4));
+    CU(ctx, dp.order.reserve((size_t)(dp.hi - dp.lo) * 4));
     PrepareParams pp;
+    pp.key = (uint32_t *)dp.key.p;
+    pp.order = (uint32_t *)dp.order.p;
     pp.pop = dp.view();
     pp.tcode = (uint4 *)dp.tcode.p;
     pp.desc = (ExprDesc *)dp.desc.p;
     pp.have_tab = want > 0 ? 1 : 0;
     pp.leaf_stride = want > 0 ? want : 0;
     launch_prepare(pp, d.stream);
-    ctx->launches++;
+    ctx->launches += 2;
     CU(ctx, cudaGetLastError());
     dp.prepared_stride = want;
     return CLOSYR_OK;
@@ -292,6 +298,11 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.chunks_per_tile = cpt;
     sp.warps = score_warps(cpt);
     sp.n_tiles = n_tiles;
+    {
+        // grouped CTA order: pays when several CTAs share an SM (short tiles); CLOSYR_ORDER=0 / 1 forces it off / on
+        static const int force = [] { const char *e = getenv("CLOSYR_ORDER"); return e ? atoi(e) : -1; }();
+        if (force == 1 || (force < 0 && sp.warps < 32)) sp.pop.order = (const uint32_t *)d.pop.order.p;
+    }
     sp.max_leafs = max_leafs;
     sp.scores = (double *)d.scores.p;
     sp.rflags = (uint8_t *)d.rflags.p;

@@ -22,6 +22,15 @@ namespace {
 using namespace dev;
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// CLOSYR_TRACE builds (scripts/build_trace.sh, never the shipped library): per-CTA phase timestamps of score_kernel
+#ifdef CLOSYR_TRACE
+constexpr int TRACE_ITEMS = 32768, TRACE_SLOTS = 16;
+__device__ unsigned long long g_trace[TRACE_ITEMS * TRACE_SLOTS];
+#define TR(k) do { if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS) g_trace[blockIdx.x * TRACE_SLOTS + (k)] = clock64(); } while (0)
+#else
+#define TR(k) do { } while (0)
+#endif
 constexpr int MAX_LEVELS = 40;
 constexpr int MAX_SCORE_WARPS = 32;  // warps per CTA = warps interpreting one staged program (runtime, power of two)
 
@@ -88,14 +97,25 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepareParams p)
     const uint32_t *gc = p.pop.code + (c0 - p.pop.code_base);
     const double *gk = p.pop.consts + (k0 - p.pop.const_base);
     TInsn *out = reinterpret_cast<TInsn *>(p.tcode) + (c0 - p.pop.code_base);
-    uint32_t pf = 0;
+    uint32_t pf = 0, fm = 0;          // fm: bit (TH_f - TH_RECIP) = the program calls the routine of function f
     for (uint32_t i = lane; i < ncode; i += 32) {
         TInsn t;
         pf |= decode_insn(gc[i], gk, k1 - k0, p.have_tab != 0, p.leaf_stride, t);
         out[i] = t;
+        // a function of the raw variable that is real everywhere comes from its table and never runs a routine
+        const uint32_t f = (t.h == TH_MOD || t.h == TH_TABC) ? ((t.aux >> 2) & 0xffu) : t.h;
+        if (f >= TH_RECIP && f < TH_COUNT) fm |= 1u << (f - TH_RECIP);
     }
     pf = __reduce_or_sync(FULL, pf);
+    fm = __reduce_or_sync(FULL, fm);
     if (lane == 0) {
+        // grouping key, heaviest routines first: programs with equal keys walk through the same code
+        auto has = [fm](uint32_t a, uint32_t b) { return ((fm >> (a - TH_RECIP)) | (fm >> (b - TH_RECIP))) & 1u; };
+        const uint32_t len = ncode / 10u;
+        p.key[e] = ((pf & (PF_NO_FAST | PF_DEEP)) ? 1u << 11 : 0u) | (has(TH_POWC, TH_POWS) | has(TH_LDZ, TH_LDSPEC)) << 10 |
+                   has(TH_LOG, TH_LOG) << 9 | has(TH_SQRT, TH_RSQRT) << 8 | has(TH_ASIN, TH_ASIN) << 7 | has(TH_ACOS, TH_ACOS) << 6 |
+                   has(TH_TAN, TH_TAN) << 5 | has(TH_EXP, TH_EXP) << 4 | has(TH_SIN, TH_COS) << 3 | has(TH_RECIP, TH_POWI) << 2 |
+                   (len < 3u ? len : 3u);
         ExprDesc d;
         d.tc_off = c0 - p.pop.code_base;
         d.ncode_pf = ncode | (pf << 16);
@@ -103,6 +123,42 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepareParams p)
         d.k_off = k0 - p.pop.const_base;
         p.desc[e] = d;
     }
+}
+
+// Counting sort of the grouping keys: order[] lists the expressions key by key (the order inside a key is whatever the
+// atomics give: a score does not depend on which CTA computes it).  One CTA; 100K expressions take ~20 us.
+__global__ void __launch_bounds__(1024) order_kernel(const uint32_t *__restrict__ key, const int64_t n, uint32_t *__restrict__ order)
+{
+    constexpr int BINS = 1 << ORDER_KEY_BITS, PER = BINS / 1024;
+    __shared__ uint32_t bins[BINS];
+    __shared__ uint32_t wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < BINS; b += 1024) bins[b] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += 1024) atomicAdd(&bins[key[i] & (BINS - 1)], 1u);
+    __syncthreads();
+    uint32_t mine[PER], tot = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { mine[k] = tot; tot += bins[tid * PER + k]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, wi, d);
+        if (lane >= d) wi += t;
+    }
+    const uint32_t base = __shfl_sync(FULL, wi - w, warp) + incl - tot;
+#pragma unroll
+    for (int k = 0; k < PER; k++) bins[tid * PER + k] = base + mine[k];
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += 1024) order[atomicAdd(&bins[key[i] & (BINS - 1)], 1u)] = (uint32_t)i;
 }
 
 // The slow half of a chunk, for the warp that owns it: some of its points were reported by the fast pass (or the chunk has
@@ -280,6 +336,9 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
     for (int j = 0; j < 4; j++)
         if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
     __syncthreads();
+#ifdef CLOSYR_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) { g_trace[blockIdx.x * TRACE_SLOTS + 11] = total; g_trace[blockIdx.x * TRACE_SLOTS + 13] = clock64(); }
+#endif
     constexpr uint32_t TASK = 32 * CPLX_POINTS;
     for (uint32_t t0 = warp * TASK; t0 < total; t0 += nwarps * TASK) {
         CplxArgs<CPLX_POINTS> ca;
@@ -297,7 +356,13 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
             if (r < total) list[r] = ((cr.nonreal >> j) & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : cr.out[j];   // NaN marks "not a real number"
         }
     }
+#ifdef CLOSYR_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) g_trace[blockIdx.x * TRACE_SLOTS + 14] = clock64();
+#endif
     __syncthreads();
+#ifdef CLOSYR_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) g_trace[blockIdx.x * TRACE_SLOTS + 15] = clock64();
+#endif
     pos -= mine;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -409,12 +474,28 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     __shared__ uint32_t s_counts[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t item = blockIdx.x;
-    const int64_t e = item / p.n_tiles;
-    const int tile = (int)(item - e * p.n_tiles);
+    const int64_t slot = item / p.n_tiles;
+    const int tile = (int)(item - slot * p.n_tiles);
+    const int64_t e = p.pop.order ? (int64_t)__ldg(p.pop.order + slot) : slot;
+    TR(1);
+#ifdef CLOSYR_TRACE
+    if (tid == 0 && blockIdx.x < TRACE_ITEMS) {
+        uint32_t smid;
+        unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_trace[blockIdx.x * TRACE_SLOTS + 0] = smid;
+        g_trace[blockIdx.x * TRACE_SLOTS + 10] = gt;
+    }
+#endif
     const uint4 dq = __ldg(reinterpret_cast<const uint4 *>(p.pop.desc + e));
     const uint32_t ncode = dq.y & 0xffffu, pflags = dq.y >> 16, meta = dq.z;
     const int leafs = (int)(meta & 0xffffu);
     const uint32_t flags = (meta >> 16) & 0xffu;
+#ifdef CLOSYR_TRACE
+    if (ncode == 0xfffff) return;
+#endif
+    TR(2);
 
     const bool too_big = leafs > p.max_leafs;                               // ops.clj:128-129
     const bool dead = (flags & (CL_F_UNSUPPORTED | CL_F_NIL)) != 0;        // eval nil / unsupported => min-score
@@ -436,6 +517,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     double *const slvl = list + nwarps * CHUNK_POINTS;
     TInsn *const tcode = reinterpret_cast<TInsn *>(slvl + ((p.chunks_per_tile + 2) & ~1));
     stage_tcode_tma(tcode, p.pop.tcode + dq.x, ncode, &s_bar, tid);
+    TR(3);
 
     const double *const sconst = p.pop.consts + dq.w;
     const uint32_t tcode_addr = smem_u32(tcode);
@@ -469,22 +551,30 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         rr.v[0] = rr.v[1] = rr.v[2] = rr.v[3] = 0.0;
         if (fast && have)
             rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+        if (r0 == 0) TR(4);
         // nothing reported anywhere in the CTA (the common round): one barrier, the fast pass has done everything
         if (fast && !__syncthreads_or(rr.ev != 0)) {
+            if (r0 == 0) TR(5);
+            if (r0 < 4 * nwarps) TR(12 + r0 / nwarps);
             warp_mx = max_nonneg(warp_mx, rr.mx);
             continue;
         }
+        if (r0 == 0) TR(5);
         const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
                                               base, valid, rr.ev, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
         nonreal += __popc(rs.nr);
         used_full |= rs.used;
         mode = rs.mode;
+        if (r0 == 0) TR(6);
+        if (r0 < 4 * nwarps) TR(12 + r0 / nwarps);
     }
+    TR(7);
     warp_mx = warp_max_nonneg(warp_mx);
     nonreal = __reduce_add_sync(FULL, nonreal);
     if (lane == 0) { s_max[warp] = warp_mx; s_nonreal[warp] = nonreal; s_full[warp] = used_full; }
     __syncthreads();
+    TR(8);
     if (warp != 0) return;
     tree_reduce_chunks(slvl, cnt, lane);
     const double tile_max = warp_max_nonneg(lane < nwarps ? s_max[lane] : 0.0);
@@ -492,6 +582,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     const uint32_t tile_full = __reduce_or_sync(FULL, lane < nwarps ? s_full[lane] : 0u);
     if (lane != 0) return;
     emit_tile(p, e, tile, leafs, is_const && !quirk_off_plus1 && tile_nonreal != 0, cnt > 0 ? slvl[0] : 0.0, tile_max, tile_nonreal, tile_full != 0);
+    TR(9);
 }
 
 // combines per-tile partials in global tile order with the same aligned binary tree, then the epilogue
@@ -669,6 +760,15 @@ __global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restric
 
 }  // namespace
 
+#ifdef CLOSYR_TRACE
+extern "C" int closyr_debug_trace(unsigned long long *out, int n_items)
+{
+    if (n_items > TRACE_ITEMS) n_items = TRACE_ITEMS;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * TRACE_SLOTS * n_items);
+}
+#endif
+
 void launch_leaf_table(const double *xs, int64_t n, int64_t stride, double *tab, void *stream)
 {
     if (stride <= 0) return;
@@ -682,6 +782,7 @@ void launch_prepare(const PrepareParams &p, void *stream)
     if (p.pop.n_expr <= 0) return;
     const int threads = 256, per_block = threads / 32;
     prepare_kernel<<<(unsigned)((p.pop.n_expr + per_block - 1) / per_block), threads, 0, (cudaStream_t)stream>>>(p);
+    order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p.key, p.pop.n_expr, p.order);
 }
 
 int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream)

@@ -23,6 +23,9 @@ struct DevPopulation {                // device pointers of one resident shard
     // program (vm.cuh TInsn, 16 bytes per ISA word, same word index relative to the shard) and one descriptor per expression
     const uint4 *tcode;
     const struct ExprDesc *desc;
+    // expression indices of the shard grouped by the handlers their programs use (order_kernel), or nullptr: the CTAs that
+    // share an SM at the same time then run through the same routines (profiles/r02_design_experiments.md, "order")
+    const uint32_t *order;
 };
 
 // one 16-byte load tells a CTA everything about its expression
@@ -39,8 +42,11 @@ struct PrepareParams {
     ExprDesc *desc;
     int32_t have_tab;                 // leaf tables exist: SRCX functions become table loads
     int64_t leaf_stride;
+    uint32_t *key;                    // [n_expr] ORDER_KEY_BITS-bit grouping key per expression (output)
+    uint32_t *order;                  // [n_expr] the counting sort of the keys (output)
 };
-void launch_prepare(const PrepareParams &p, void *stream);
+constexpr int ORDER_KEY_BITS = 12;
+void launch_prepare(const PrepareParams &p, void *stream);     // prepare_kernel + order_kernel
 
 struct ScoreParams {
     DevPopulation pop;

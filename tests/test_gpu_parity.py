@@ -485,6 +485,29 @@ def test_ranking_a_million_scores_with_ties(ctx):
     assert top.tolist() == want[:100].tolist()
 
 
+def test_grouped_cta_order_does_not_change_a_score():
+    """score_kernel takes its expressions in the grouped order of order_kernel when several CTAs share an SM
+    (kernels.cu); CLOSYR_ORDER=0 / 1 forces it off / on (read once per process).  Scores and flags are bit-identical."""
+    import os, subprocess, sys, hashlib
+    prog = (
+        "import sys, hashlib, numpy as np; sys.path.insert(0, '.'); import closyr_b200 as cb\n"
+        "b = cb.PopulationBuilder(); b.generate(4242, 5000, 40, 0)\n"
+        "ctx = cb.Context([0]); out = []\n"
+        "for n in (130, 1024, 5000):\n"
+        "    xs = 0.7 * np.arange(n) / n; ys = np.cos(xs); ctx.set_points(xs, ys)\n"
+        "    s, f = ctx.score_batch(b.view(), 40)\n"
+        "    out.append(hashlib.sha256(np.asarray(s).tobytes() + np.asarray(f).tobytes()).hexdigest())\n"
+        "print(' '.join(out))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = []
+    for force in ("0", "1"):
+        env = dict(os.environ, CLOSYR_ORDER=force)
+        r = subprocess.run([sys.executable, "-c", prog], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got.append(r.stdout.strip().splitlines()[-1])
+    assert got[0] == got[1] and len(got[0].split()) == 3
+
+
 def test_zz_parity_report():
     """Prints what the population checks of this session saw (pytest -s)."""
     for rec in PARITY_REPORT:
