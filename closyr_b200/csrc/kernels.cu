@@ -340,7 +340,10 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
     if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) { g_trace[blockIdx.x * TRACE_SLOTS + 11] = total; g_trace[blockIdx.x * TRACE_SLOTS + 13] = clock64(); }
 #endif
     constexpr uint32_t TASK = 32 * CPLX_POINTS;
-    for (uint32_t t0 = warp * TASK; t0 < total; t0 += nwarps * TASK) {
+    for (uint32_t tb = 0; tb < total; tb += nwarps * TASK) {
+        if (tb) __syncthreads();                                                 // the passes of a round start in step
+        const uint32_t t0 = tb + warp * TASK;
+        if (t0 >= total) continue;
         CplxArgs<CPLX_POINTS> ca;
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
