@@ -793,8 +793,10 @@ int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream)
     const int64_t items = p.pop.n_expr * p.n_tiles;
     if (items <= 0) return 0;
     // [warp slots | compaction list | chunk sums + a scratch word | threaded code + the entry the dispatch loop prefetches past END]
+    // CLOSYR_SMEM_PAD (bytes): fewer CTAs per SM, a knob for measurements (profiles/r02_design_experiments.md), not an API
+    static const size_t pad = [] { const char *e = getenv("CLOSYR_SMEM_PAD"); return e ? (size_t)atol(e) : 0; }();
     const size_t smem = (size_t)p.warps * (SLOT_DOUBLES_PER_WARP + CHUNK_POINTS) * 8 + (size_t)((p.chunks_per_tile + 2) & ~1) * 8 +
-                        ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16;
+                        ((size_t)max_code_words + 1) * sizeof(dev::TInsn) + 16 + pad;
     // opt in to > 48 KiB of dynamic shared memory; the attribute is per device, so it is set at every launch
     if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     score_kernel<<<(unsigned)items, p.warps * 32, smem, (cudaStream_t)stream>>>(p);
