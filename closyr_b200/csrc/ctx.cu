@@ -96,6 +96,7 @@ struct DevPop {                       // one resident population shard
     DevBuf code, code_off, consts, const_off, meta, aux;
     DevBuf tcode, desc;               // what prepare_kernel derives from the arrays above (threaded code, descriptors)
     DevBuf key, order;                // grouping keys and the expression order made from them (order_kernel)
+    bool ordered = false;             // `order` holds the order of the current threaded code (made on first use)
     int64_t prepared_stride = -2;     // leaf_stride the threaded code was made for (-1: without tables, -2: not made yet)
     int64_t lo = 0, hi = 0;           // expression range of the caller's population held here
     uint32_t code_base = 0, const_base = 0, max_code = 0, max_consts = 0, n_words = 0;
@@ -235,17 +236,16 @@ int prepare_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, int64_t leaf_stri
     CU(ctx, dp.tcode.reserve((size_t)dp.n_words * 16 + 16));
     CU(ctx, dp.desc.reserve((size_t)(dp.hi - dp.lo) * sizeof(ExprDesc)));
     CU(ctx, dp.key.reserve((size_t)(dp.hi - dp.lo) * 4));
-    CU(ctx, dp.order.reserve((size_t)(dp.hi - dp.lo) * 4));
     PrepareParams pp;
     pp.key = (uint32_t *)dp.key.p;
-    pp.order = (uint32_t *)dp.order.p;
     pp.pop = dp.view();
     pp.tcode = (uint4 *)dp.tcode.p;
     pp.desc = (ExprDesc *)dp.desc.p;
     pp.have_tab = want > 0 ? 1 : 0;
     pp.leaf_stride = want > 0 ? want : 0;
     launch_prepare(pp, d.stream);
-    ctx->launches += 2;
+    ctx->launches++;
+    dp.ordered = false;
     CU(ctx, cudaGetLastError());
     dp.prepared_stride = want;
     return CLOSYR_OK;
@@ -301,7 +301,16 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     {
         // grouped CTA order: pays when several CTAs share an SM (short tiles); CLOSYR_ORDER=0 / 1 forces it off / on
         static const int force = [] { const char *e = getenv("CLOSYR_ORDER"); return e ? atoi(e) : -1; }();
-        if (force == 1 || (force < 0 && sp.warps < 32)) sp.pop.order = (const uint32_t *)d.pop.order.p;
+        if (force == 1 || (force < 0 && sp.warps < 32)) {
+            if (!d.pop.ordered) {
+                CU(ctx, d.pop.order.reserve((size_t)ne * 4));
+                launch_order((const uint32_t *)d.pop.key.p, ne, (uint32_t *)d.pop.order.p, d.stream);
+                ctx->launches++;
+                CU(ctx, cudaGetLastError());
+                d.pop.ordered = true;
+            }
+            sp.pop.order = (const uint32_t *)d.pop.order.p;
+        }
     }
     sp.max_leafs = max_leafs;
     sp.scores = (double *)d.scores.p;

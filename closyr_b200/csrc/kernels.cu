@@ -785,7 +785,12 @@ void launch_prepare(const PrepareParams &p, void *stream)
     if (p.pop.n_expr <= 0) return;
     const int threads = 256, per_block = threads / 32;
     prepare_kernel<<<(unsigned)((p.pop.n_expr + per_block - 1) / per_block), threads, 0, (cudaStream_t)stream>>>(p);
-    order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p.key, p.pop.n_expr, p.order);
+}
+
+void launch_order(const uint32_t *key, int64_t n_expr, uint32_t *order, void *stream)
+{
+    if (n_expr <= 0) return;
+    order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(key, n_expr, order);
 }
 
 int launch_score(const ScoreParams &p, uint32_t max_code_words, void *stream)

@@ -43,10 +43,11 @@ struct PrepareParams {
     int32_t have_tab;                 // leaf tables exist: SRCX functions become table loads
     int64_t leaf_stride;
     uint32_t *key;                    // [n_expr] ORDER_KEY_BITS-bit grouping key per expression (output)
-    uint32_t *order;                  // [n_expr] the counting sort of the keys (output)
 };
 constexpr int ORDER_KEY_BITS = 12;
-void launch_prepare(const PrepareParams &p, void *stream);     // prepare_kernel + order_kernel
+void launch_prepare(const PrepareParams &p, void *stream);
+// order[] = the expressions of a shard key by key (counting sort of prepare_kernel's keys), for DevPopulation::order
+void launch_order(const uint32_t *key, int64_t n_expr, uint32_t *order, void *stream);
 
 struct ScoreParams {
     DevPopulation pop;
