@@ -764,6 +764,11 @@ __global__ void __launch_bounds__(128) leaf_table_kernel(const double *__restric
 }  // namespace
 
 #ifdef CLOSYR_TRACE
+extern "C" int closyr_debug_ztags(unsigned long long *out)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, dev::g_ztags, sizeof(unsigned long long) * 8);
+}
 extern "C" int closyr_debug_trace(unsigned long long *out, int n_items)
 {
     if (n_items > TRACE_ITEMS) n_items = TRACE_ITEMS;

@@ -947,7 +947,29 @@ __device__ __forceinline__ void c_mul(CAcc<P> &a, const double (&sre)[P], const 
     CLOSYR_FORJ { a.re[j] = rr[j]; a.im[j] = ri[j]; }
 }
 
+#ifdef CLOSYR_TRACE
+__device__ unsigned long long g_ztags[8];
+#define CLOSYR_ZSTAT()                                                                                   \
+    {                                                                                                    \
+        const int t0_ = ztag(zv(a.re[0], a.im[0])), t1_ = ztag(zv(a.re[1], a.im[1]));                     \
+        const unsigned both_ = __ballot_sync(0xffffffffu, t0_ == T_CPLX && t1_ == T_CPLX);                \
+        const unsigned none_ = __ballot_sync(0xffffffffu, t0_ != T_CPLX && t1_ != T_CPLX);                \
+        const unsigned real_ = __ballot_sync(0xffffffffu, t0_ == T_REAL && t1_ == T_REAL);                \
+        if ((threadIdx.x & 31) == 0) {                                                                   \
+            atomicAdd(&g_ztags[0], 1ull);                                                                \
+            if (both_ == 0xffffffffu) atomicAdd(&g_ztags[1], 1ull);                                      \
+            else if (none_ == 0xffffffffu) atomicAdd(&g_ztags[2], 1ull);                                 \
+            else atomicAdd(&g_ztags[3], 1ull);                                                           \
+            atomicAdd(&g_ztags[4], (unsigned long long)__popc(both_));                                   \
+            atomicAdd(&g_ztags[5], (unsigned long long)__popc(none_));                                   \
+            atomicAdd(&g_ztags[6], (unsigned long long)__popc(real_));                                   \
+        }                                                                                                \
+    }
+#else
+#define CLOSYR_ZSTAT()
+#endif
 #define CLOSYR_ZCALL(f)                                            \
+    CLOSYR_ZSTAT()                                                 \
     CLOSYR_FORJ {                                                  \
         const Z r_ = f(zv(a.re[j], a.im[j]));                      \
         a.re[j] = r_.re;                                           \
@@ -1105,6 +1127,14 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
 #pragma unroll 1
     for (;;) {
         uint32_t h, aux, clo, chi;
+        if (cmo) {
+            // back to real mode as soon as no point of the warp has an imaginary part (a square, an absolute value, a chopped
+            // sum): that IS real mode's invariant (reals, directed infinities, Indeterminate = NaN with a zero imaginary part;
+            // ComplexInfinity has one), and half of the complex-mode function calls of the GA mix had such operands
+            bool real_ = true;
+            CLOSYR_FORJ real_ = real_ && a.im[j] == 0.0;
+            if (__all_sync(FULLW, real_)) cmo = 0;
+        }
         if (!DEEP && cmo == 0) {
             asm volatile(
                 "{\n\t"
