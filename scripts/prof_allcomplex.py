@@ -24,4 +24,5 @@ with open("gpurun_out/allcomplex.txt", "w") as fo:
     fo.write("%d of %d expressions report >= 3073 of 4096 points\n" % (len(idx), pop))
     for i in idx:
         fo.write("%d\t%d\t%s\n" % (i, tot[i], texts[i]))
+np.save("gpurun_out/reported_first_round.npy", np.stack([tot, full.astype(np.int64), t[:, 9] - t[:, 1]], 1))
 print(len(idx))
