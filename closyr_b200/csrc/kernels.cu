@@ -291,7 +291,7 @@ __device__ __forceinline__ double warp_max_nonneg(double m)
 // Every warp first runs the IEEE-real fast path on its chunk.  The points it reports are compacted across
 // the WHOLE CTA into one list and re-evaluated with the complete algebra, 64 points (2 per lane) per warp and
 // pass -- so the extra work of a chunk that left the real line is shared by all warps instead of stalling the
-// CTA behind one of them.  `mode` is the CTA's adaptive state: when most points of the previous round needed
+// CTA behind one of them.  `mode` is the CTA's adaptive state: when more than half of the points of the previous round needed
 // the complete algebra the fast pass is skipped.  Both evaluators give bit-identical values wherever the fast
 // path is valid, so the heuristic cannot change a score.
 // Must be called by every thread of the CTA (it contains __syncthreads).
@@ -375,7 +375,7 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
             else res.v[j] = r;
         }
     }
-    res.mode = (total * 4u >= (uint32_t)blockDim.x * 4u * 3u) ? 1u : 0u;      // >= 75 % of the round's points
+    res.mode = (total * 2u > (uint32_t)blockDim.x * 4u) ? 1u : 0u;               // more than half of the round's points: two passes anyway
     return res;
 }
 
