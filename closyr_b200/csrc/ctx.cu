@@ -187,31 +187,20 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     if (ne <= 0) return CLOSYR_OK;
     dp.code_base = pop->code_off[lo];
     dp.const_base = pop->const_off[lo];
-    const size_t ncode = pop->code_off[hi] - dp.code_base, nk = pop->const_off[hi] - dp.const_base;
-    uint32_t mc = 0, mk = 0;
     // the layout the kernel's TMA staging depends on (include/closyr_b200.h): every program starts on a 16-byte
     // boundary and is a whole number of 16-byte units; offsets never decrease.  A violation would be a misaligned
     // bulk copy (sticky context error) or a wrapped size, so it is refused here.
-    if (pop->code_off[hi] % 4u != 0 || pop->const_off[hi] % 2u != 0)
+    if (pop->code_off[hi] % 4u != 0 || pop->const_off[hi] % 2u != 0) {
+        dp.hi = dp.lo;
         return fail(ctx, CLOSYR_E_ARG, "population layout: code_off must be a multiple of 4 words, const_off of 2 doubles");
-    for (int64_t e = lo; e < hi; e++) {
-        const uint32_t c0 = pop->code_off[e], c1 = pop->code_off[e + 1], k0 = pop->const_off[e], k1 = pop->const_off[e + 1];
-        if (c0 % 4u != 0 || k0 % 2u != 0)
-            return fail(ctx, CLOSYR_E_ARG, "population layout: code_off must be a multiple of 4 words, const_off of 2 doubles (expression " + std::to_string(e) + ")");
-        if (c1 < c0 || k1 < k0)
-            return fail(ctx, CLOSYR_E_ARG, "population layout: offsets must not decrease (expression " + std::to_string(e) + ")");
-        if (c1 == c0)
-            return fail(ctx, CLOSYR_E_ARG, "population layout: empty program (expression " + std::to_string(e) + "); a program ends with CL_END");
-        if ((pop->code[c1 - 1] & 0xffu) != CL_END)
-            return fail(ctx, CLOSYR_E_ARG, "population layout: program does not end with CL_END (expression " + std::to_string(e) + ")");
-        mc = std::max(mc, c1 - c0);
-        mk = std::max(mk, k1 - k0);
     }
-    if (mc > CLOSYR_MAX_CODE_WORDS || mk > CLOSYR_MAX_CONSTS)
-        return fail(ctx, CLOSYR_E_ARG, "population holds a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS");
-    dp.max_code = mc;
-    dp.max_consts = mk;
-    dp.n_words = (uint32_t)ncode;
+    if (pop->code_off[hi] < dp.code_base || pop->const_off[hi] < dp.const_base) {
+        dp.hi = dp.lo;
+        return fail(ctx, CLOSYR_E_ARG, "population layout: offsets must not decrease");
+    }
+    const size_t ncode = pop->code_off[hi] - dp.code_base, nk = pop->const_off[hi] - dp.const_base;
+    // the copies first: the DMA engine moves the arrays while the host walks the offsets below (0.5 ms per 100K
+    // expressions).  Nothing is launched on the shard before the walk has accepted it.
     CU(ctx, dp.code.reserve(ncode * 4 + 16));
     CU(ctx, dp.consts.reserve(nk * 8 + 16));
     CU(ctx, dp.code_off.reserve((ne + 1) * 4));
@@ -224,6 +213,30 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     CU(ctx, cudaMemcpyAsync(dp.const_off.p, pop->const_off + lo, (ne + 1) * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.meta.p, pop->meta + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.aux.p, pop->aux + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
+    uint32_t mc = 0, mk = 0;
+    const char *bad = nullptr;
+    int64_t bad_e = -1;
+    for (int64_t e = lo; e < hi && !bad; e++) {
+        const uint32_t c0 = pop->code_off[e], c1 = pop->code_off[e + 1], k0 = pop->const_off[e], k1 = pop->const_off[e + 1];
+        if (c0 % 4u != 0 || k0 % 2u != 0) bad = "code_off must be a multiple of 4 words, const_off of 2 doubles";
+        else if (c1 < c0 || k1 < k0 || c1 > pop->code_off[hi] || k1 > pop->const_off[hi]) bad = "offsets must not decrease";
+        else if (c1 == c0) bad = "empty program; a program ends with CL_END";
+        else if ((pop->code[c1 - 1] & 0xffu) != CL_END) bad = "program does not end with CL_END";
+        if (bad) bad_e = e;
+        else {
+            mc = std::max(mc, c1 - c0);
+            mk = std::max(mk, k1 - k0);
+        }
+    }
+    if (!bad && (mc > CLOSYR_MAX_CODE_WORDS || mk > CLOSYR_MAX_CONSTS)) bad = "a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS";
+    if (bad) {
+        cudaStreamSynchronize(d.stream);          // the copies read the caller's arrays
+        dp.hi = dp.lo;                            // nothing resident
+        return fail(ctx, CLOSYR_E_ARG, std::string("population layout: ") + bad + (bad_e >= 0 ? " (expression " + std::to_string(bad_e) + ")" : ""));
+    }
+    dp.max_code = mc;
+    dp.max_consts = mk;
+    dp.n_words = (uint32_t)ncode;
     return CLOSYR_OK;
 }
 

@@ -508,6 +508,52 @@ def test_grouped_cta_order_does_not_change_a_score():
     assert got[0] == got[1] and len(got[0].split()) == 3
 
 
+def test_malformed_layouts_are_refused_and_the_context_stays_usable(ctx):
+    """upload_shard starts the host-to-device copies first and walks the offsets while the DMA runs; a layout the TMA
+    staging could not take (include/closyr_b200.h: 16-byte aligned programs, monotonic offsets, CL_END last) must come back
+    as CLOSYR_E_ARG with nothing launched, and the next valid call must work (no sticky CUDA error)."""
+    import ctypes as C
+    xs, ys = synth_points(300)
+    ctx.set_points(xs, ys)
+    b = cb.PopulationBuilder()
+    b.generate(77, 64, 40, 0)
+    good_scores, good_flags = ctx.score_batch(b.view(), 40)
+    a = b.arrays()
+
+    def population(arr):
+        keep = {k: np.ascontiguousarray(v) for k, v in arr.items()}
+        pop = L.Population()
+        pop.n_expr = len(keep["meta"])
+        pop.code = keep["code"].ctypes.data_as(C.POINTER(C.c_uint32))
+        pop.code_off = keep["code_off"].ctypes.data_as(C.POINTER(C.c_uint32))
+        pop.consts = keep["consts"].ctypes.data_as(C.POINTER(C.c_double))
+        pop.const_off = keep["const_off"].ctypes.data_as(C.POINTER(C.c_uint32))
+        pop.meta = keep["meta"].ctypes.data_as(C.POINTER(C.c_uint32))
+        pop.aux = keep["aux"].ctypes.data_as(C.POINTER(C.c_uint32))
+        return pop, keep
+
+    def broken(edit):
+        arr = {k: v.copy() for k, v in a.items()}
+        edit(arr)
+        return population(arr)
+
+    def misaligned(arr): arr["code_off"][5] += 1
+    def decreasing(arr): arr["code_off"][7] = arr["code_off"][5]
+    def empty_program(arr): arr["code_off"][9] = arr["code_off"][8]
+    def no_end(arr): arr["code"][arr["code_off"][4] - 1] = 9          # CL_NEG where CL_END must be
+    def odd_consts(arr): arr["const_off"][3] += 1
+    for edit in (misaligned, decreasing, empty_program, no_end, odd_consts):
+        pop, keep = broken(edit)
+        with pytest.raises(L.ClosyrError) as err:
+            ctx.score_batch(pop, 40)
+        assert "population layout" in str(err.value), (edit.__name__, str(err.value))
+        s, f = ctx.score_batch(b.view(), 40)
+        assert s.tolist() == good_scores.tolist() and f.tolist() == good_flags.tolist(), edit.__name__
+    pop, keep = population(a)                                             # the same arrays untouched: accepted
+    s, f = ctx.score_batch(pop, 40)
+    assert s.tolist() == good_scores.tolist()
+
+
 def test_zz_parity_report():
     """Prints what the population checks of this session saw (pytest -s)."""
     for rec in PARITY_REPORT:
