@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/closyr_b200.h"
@@ -213,20 +214,40 @@ int upload_shard(closyr_ctx *ctx, DeviceState &d, DevPop &dp, const closyr_popul
     CU(ctx, cudaMemcpyAsync(dp.const_off.p, pop->const_off + lo, (ne + 1) * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.meta.p, pop->meta + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaMemcpyAsync(dp.aux.p, pop->aux + lo, ne * 4, cudaMemcpyHostToDevice, d.stream));
+    // the walk over the offsets (it streams the whole code array through the host caches for the CL_END test): a few
+    // threads for a large shard, each over its own stretch; the first offending expression is reported
+    struct Walk { uint32_t mc = 0, mk = 0; const char *bad = nullptr; int64_t bad_e = -1; };
+    const uint32_t code_end = pop->code_off[hi], const_end = pop->const_off[hi];
+    auto walk = [pop, code_end, const_end](int64_t a, int64_t b, Walk *w) {
+        for (int64_t e = a; e < b && !w->bad; e++) {
+            const uint32_t c0 = pop->code_off[e], c1 = pop->code_off[e + 1], k0 = pop->const_off[e], k1 = pop->const_off[e + 1];
+            if (c0 % 4u != 0 || k0 % 2u != 0) w->bad = "code_off must be a multiple of 4 words, const_off of 2 doubles";
+            else if (c1 < c0 || k1 < k0 || c1 > code_end || k1 > const_end) w->bad = "offsets must not decrease";
+            else if (c1 == c0) w->bad = "empty program; a program ends with CL_END";
+            else if ((pop->code[c1 - 1] & 0xffu) != CL_END) w->bad = "program does not end with CL_END";
+            if (w->bad) w->bad_e = e;
+            else {
+                w->mc = std::max(w->mc, c1 - c0);
+                w->mk = std::max(w->mk, k1 - k0);
+            }
+        }
+    };
+    const int nt = ne >= 32768 ? (int)std::min<unsigned>(4u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    Walk parts[4];
+    if (nt == 1) walk(lo, hi, &parts[0]);
+    else {
+        std::thread th[3];
+        for (int t = 1; t < nt; t++) th[t - 1] = std::thread(walk, lo + ne * t / nt, lo + ne * (t + 1) / nt, &parts[t]);
+        walk(lo, lo + ne / nt, &parts[0]);
+        for (int t = 1; t < nt; t++) th[t - 1].join();
+    }
     uint32_t mc = 0, mk = 0;
     const char *bad = nullptr;
     int64_t bad_e = -1;
-    for (int64_t e = lo; e < hi && !bad; e++) {
-        const uint32_t c0 = pop->code_off[e], c1 = pop->code_off[e + 1], k0 = pop->const_off[e], k1 = pop->const_off[e + 1];
-        if (c0 % 4u != 0 || k0 % 2u != 0) bad = "code_off must be a multiple of 4 words, const_off of 2 doubles";
-        else if (c1 < c0 || k1 < k0 || c1 > pop->code_off[hi] || k1 > pop->const_off[hi]) bad = "offsets must not decrease";
-        else if (c1 == c0) bad = "empty program; a program ends with CL_END";
-        else if ((pop->code[c1 - 1] & 0xffu) != CL_END) bad = "program does not end with CL_END";
-        if (bad) bad_e = e;
-        else {
-            mc = std::max(mc, c1 - c0);
-            mk = std::max(mk, k1 - k0);
-        }
+    for (int t = 0; t < nt; t++) {
+        mc = std::max(mc, parts[t].mc);
+        mk = std::max(mk, parts[t].mk);
+        if (!bad && parts[t].bad) { bad = parts[t].bad; bad_e = parts[t].bad_e; }
     }
     if (!bad && (mc > CLOSYR_MAX_CODE_WORDS || mk > CLOSYR_MAX_CONSTS)) bad = "a program above CLOSYR_MAX_CODE_WORDS / CLOSYR_MAX_CONSTS";
     if (bad) {
