@@ -80,10 +80,10 @@ __device__ __forceinline__ double m_recip(double x) { return 1.0 / x; }
 __device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
 
 // the library routines that have no lean version: one copy each, called by both evaluators
-__device__ __noinline__ double m_tan(double x) { return tan(x); }
+__device__ __noinline__ double m_tan(double x) { return vm_special(x) ? vm_nan_of(x) : tan(x); }       // tan(Inf), tan(NaN): no argument reduction
 __device__ __noinline__ double m_asin(double x) { return asin(x); }
 __device__ __noinline__ double m_acos(double x) { return acos(x); }
-__device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double m_pow(double x, double y) { return (x != x && y == y && y != 0.0) ? x : pow(x, y); }   // NaN^y
 
 // sinh and cosh of the same argument (the complex sin / cos / tan need both): one exponential where that is
 // accurate (0.5 <= |y| < 700: e - 1/e cancels at most one bit there), the library routines elsewhere
