@@ -553,7 +553,9 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         rr.mx = 0.0;
         rr.v[0] = rr.v[1] = rr.v[2] = rr.v[3] = 0.0;
         if (fast && have)
-            rr = run_real<4>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
+            rr = nwarps < MAX_SCORE_WARPS
+                     ? run_real<4, true>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr)
+                     : run_real<4, false>(tcode_addr, slot_addr, p.xs + base, p.leaf_tab ? p.leaf_tab + base : nullptr, p.ys + base, valid, sum_addr);
         if (r0 == 0) TR(4);
         // nothing reported anywhere in the CTA (the common round): one barrier, the fast pass has done everything
         if (fast && !__syncthreads_or(rr.ev != 0)) {

@@ -769,7 +769,11 @@ __device__ __forceinline__ double chunk_residuals(const double (&v)[4], const do
     "mov.b32 %5, h" S "_;\n\t mov.b32 %6, aux" S "_;\n\t mov.b32 %7, lo" S "_;\n\t mov.b32 %8, hi" S "_;\n\t" \
     "bra.uni OUT_;\n\t"
 
-template <int P>
+// LEAN = ONE copy of the PTX block, without the prefetch of the next entry: for CTAs of fewer than 32 warps.  Several programs
+// share an SM then and the launch is bound by the instruction cache the SMs of a GPC share (profiles/
+// r02_design_experiments.md, "instruction supply"): 2.4 KB less code per expression are worth more than the prefetch
+// (100K x 256 / 1024 points -2 %, one program per SM +4 %).
+template <int P, bool LEAN>
 __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const uint32_t slot_addr,
                                                const double *__restrict__ xp, const double *__restrict__ tab,
                                                const double *__restrict__ yp, const uint32_t valid, const uint32_t sum_addr)
@@ -805,20 +809,34 @@ __device__ __noinline__ RealResult<P> run_real(const uint32_t tcode_addr, const 
 #pragma unroll 1
     for (;;) {
         uint32_t h, aux, clo, chi;
-        asm volatile(
-            "{\n\t"
-            ".reg .b32 t_, hA_, auxA_, loA_, hiA_, hB_, auxB_, loB_, hiB_;\n\t"
-            ".reg .b64 ad_;\n\t"
-            ".reg .f64 c_, s0_, s1_, s2_, s3_;\n\t"
-            "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%4];\n\t"
-            "bra.uni NEXT_A;\n\t"
-            CLOSYR_CHEAP_HANDLERS("A", "B", "+16")
-            CLOSYR_CHEAP_HANDLERS("B", "A", "+16")
-            "OUT_:\n\t"
-            "}\n"
-            : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+r"(ip), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
-            : "r"(slot_addr), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "l"(tab)
-            : "memory");
+        if (LEAN)
+            asm volatile(
+                "{\n\t"
+                ".reg .b32 t_, hA_, auxA_, loA_, hiA_;\n\t"
+                ".reg .b64 ad_;\n\t"
+                ".reg .f64 c_, s0_, s1_, s2_, s3_;\n\t"
+                "bra.uni NEXT_A;\n\t"
+                CLOSYR_CHEAP_HANDLERS("A", "A", "")
+                "OUT_:\n\t"
+                "}\n"
+                : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+r"(ip), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
+                : "r"(slot_addr), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "l"(tab)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t"
+                ".reg .b32 t_, hA_, auxA_, loA_, hiA_, hB_, auxB_, loB_, hiB_;\n\t"
+                ".reg .b64 ad_;\n\t"
+                ".reg .f64 c_, s0_, s1_, s2_, s3_;\n\t"
+                "ld.shared.v4.b32 {hA_, auxA_, loA_, hiA_}, [%4];\n\t"
+                "bra.uni NEXT_A;\n\t"
+                CLOSYR_CHEAP_HANDLERS("A", "B", "+16")
+                CLOSYR_CHEAP_HANDLERS("B", "A", "+16")
+                "OUT_:\n\t"
+                "}\n"
+                : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+r"(ip), "=&r"(h), "=&r"(aux), "=&r"(clo), "=&r"(chi)
+                : "r"(slot_addr), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "l"(tab)
+                : "memory");
         const double c = __hiloint2double((int)chi, (int)clo);
     redo:
         switch (h) {
