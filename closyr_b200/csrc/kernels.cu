@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepareParams p)
     }
     pf = __reduce_or_sync(FULL, pf);
     fm = __reduce_or_sync(FULL, fm);
+    {
+        constexpr uint32_t DOMAIN = 1u << (TH_SQRT - TH_RECIP) | 1u << (TH_RSQRT - TH_RECIP) | 1u << (TH_POWC - TH_RECIP) | 1u << (TH_LOG - TH_RECIP) |
+                                    1u << (TH_ASIN - TH_RECIP) | 1u << (TH_ACOS - TH_RECIP) | 1u << (TH_LDZ - TH_RECIP) | 1u << (TH_LDSPEC - TH_RECIP) |
+                                    1u << (TH_POWS - TH_RECIP);
+        if (fm & DOMAIN) pf |= PF_DOMAIN;
+    }
     if (lane == 0) {
         // grouping key, heaviest routines first: programs with equal keys walk through the same code
         auto has = [fm](uint32_t a, uint32_t b) { return ((fm >> (a - TH_RECIP)) | (fm >> (b - TH_RECIP))) & 1u; };
@@ -300,14 +306,14 @@ struct Round {
     uint32_t *counts;      // [2][32] reported points per warp, double-buffered by round parity
 };
 
-struct CplxPassResult { double v[4]; uint32_t nr, mode; };
+struct CplxPassResult { double v[4]; uint32_t nr, mode, used; };
 
 // The cold half of a round: some point of the CTA was reported.  A function of its own so that the state it needs
 // does not live in the registers of the common path.
 __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ sconst, const uint32_t tcode_addr,
                                                  const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                  double *__restrict__ list, uint32_t *__restrict__ cnt,
-                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev,
+                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev, const bool ran_fast,
                                                  const double v0, const double v1, const double v2, const double v3)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -340,6 +346,7 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
     if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) { g_trace[blockIdx.x * TRACE_SLOTS + 11] = total; g_trace[blockIdx.x * TRACE_SLOTS + 13] = clock64(); }
 #endif
     constexpr uint32_t TASK = 32 * CPLX_POINTS;
+    uint32_t left = 0;                                                             // a task of this warp left real mode
     for (uint32_t tb = 0; tb < total; tb += nwarps * TASK) {
         if (tb) __syncthreads();                                                 // the passes of a round start in step
         const uint32_t t0 = tb + warp * TASK;
@@ -352,6 +359,7 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
         }
         const CplxResult<CPLX_POINTS> cr = deep ? run_cplx<CPLX_POINTS, true>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab)
                                                 : run_cplx<CPLX_POINTS, false>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
+        left |= cr.left_real;
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
@@ -362,7 +370,7 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
 #ifdef CLOSYR_TRACE
     if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) g_trace[blockIdx.x * TRACE_SLOTS + 14] = clock64();
 #endif
-    __syncthreads();
+    const uint32_t nleft = (uint32_t)__syncthreads_count(lane == 0 && left != 0);   // warps with a task that left real mode
 #ifdef CLOSYR_TRACE
     if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) g_trace[blockIdx.x * TRACE_SLOTS + 15] = clock64();
 #endif
@@ -375,7 +383,14 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
             else res.v[j] = r;
         }
     }
-    res.mode = (total * 2u > (uint32_t)blockDim.x * 4u) ? 1u : 0u;               // more than half of the round's points: two passes anyway
+    // the next round of the tile (points are sorted by x, neighbouring rounds behave alike).  After a fast pass: skip it next time
+    // when more than half of the round's points were reported -- two passes of the complete algebra are certain then.  After
+    // a round without one: try it again when most of the warps' tasks never left real mode.
+    {
+        const uint32_t busy = (total + TASK - 1) / TASK < (uint32_t)nwarps ? (total + TASK - 1) / TASK : (uint32_t)nwarps;
+        res.mode = ran_fast ? ((total * 2u > (uint32_t)blockDim.x * 4u) ? 1u : 0u) : ((nleft * 2u > busy) ? 1u : 0u);
+    }
+    res.used = nleft != 0 ? 1u : 0u;
     return res;
 }
 
@@ -389,7 +404,7 @@ __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sc
                                                    const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                    double *__restrict__ list, uint32_t *__restrict__ cnt,
                                                    const double *__restrict__ xs, const double *__restrict__ ys,
-                                                   const int64_t base, const uint32_t valid, const uint32_t ev_in,
+                                                   const int64_t base, const uint32_t valid, const uint32_t ev_in, const bool ran_fast,
                                                    const uint32_t quirk_off_plus1, const uint32_t sum_addr,
                                                    const double v0, const double v1, const double v2, const double v3)
 {
@@ -402,10 +417,10 @@ __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sc
 #pragma unroll
         for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? sconst[quirk_off_plus1 - 1 + base + j] : 0.0;
     }
-    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, deep, list, cnt, xs, base, ev, v[0], v[1], v[2], v[3]);
+    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, deep, list, cnt, xs, base, ev, ran_fast, v[0], v[1], v[2], v[3]);
     out.nr = cp.nr;
     out.mode = cp.mode;
-    out.used = __any_sync(FULL, ev != 0) ? 1u : 0u;
+    out.used = cp.used;                          // the complete algebra was NEEDED: some evaluation left the real line
     out.mx = 0.0;
 #pragma unroll
     for (int j = 0; j < 4; j++) out.v[j] = cp.v[j];
@@ -538,7 +553,10 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
     const uint32_t slvl_addr = smem_u32(slvl);
     const bool fast_ok = !is_const && !(pflags & PF_NO_FAST);
     double warp_mx = 0.0;
-    uint32_t nonreal = 0, mode = 0, parity = 0, used_full = 0;
+    // a program that calls a function with a real domain starts WITHOUT the fast pass: three of four such programs of the GA
+    // mix leave the real line somewhere, and then the fast pass is code and time on top of the complete algebra
+    // (profiles/r02_design_experiments.md, "the fast pass as a choice per program")
+    uint32_t nonreal = 0, mode = (pflags & PF_DOMAIN) ? 1u : 0u, parity = 0, used_full = 0;
     for (int r0 = 0; r0 < cnt; r0 += nwarps, parity ^= 1u) {
         const int ci = r0 + warp;
         const bool have = ci < cnt;
@@ -566,7 +584,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         }
         if (r0 == 0) TR(5);
         const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
-                                              base, valid, rr.ev, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
+                                              base, valid, rr.ev, fast, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
         nonreal += __popc(rs.nr);
         used_full |= rs.used;

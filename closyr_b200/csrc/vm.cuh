@@ -447,6 +447,7 @@ static_assert(TH_CHEAP == 19 && TH_COUNT == 36, "the branch-target tables of the
 // program properties found while decoding
 constexpr uint32_t PF_NO_FAST = 1u;   // an instruction the IEEE fast path cannot express: every point takes run_cplx
 constexpr uint32_t PF_DEEP = 2u;      // uses spill slots >= CLOSYR_REG_SLOTS (kept in local memory by run_cplx)
+constexpr uint32_t PF_DOMAIN = 4u;    // calls a function with a real domain (sqrt log asin acos x^c ...): 3 of 4 such programs of the GA mix leave the real line somewhere
 
 // handler of the elementary function CL_NEG + i
 __constant__ uint8_t closyr_th_of_function[CL_ABS - CL_NEG + 1] = {

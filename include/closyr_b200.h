@@ -98,7 +98,7 @@ enum closyr_opcode {
 /* result flags written per expression by closyr_score_batch */
 #define CL_R_TOO_BIG 0x01        /* leafs > max-leafs => min-score (ops.clj:128-129)                   */
 #define CL_R_MIN_SCORE 0x02      /* nil / throwing eval => min-score (ops.clj:131-136)                 */
-#define CL_R_FULL_SEMANTICS 0x04 /* at least one 128-point chunk left the IEEE-real fast path          */
+#define CL_R_FULL_SEMANTICS 0x04 /* diagnostic: some point's evaluation left the real line (complex values, ComplexInfinity) */
 
 /*
  * The population: one flat struct-of-arrays buffer (north star (1)).  Programs are concatenated;
