@@ -313,31 +313,40 @@ struct CplxPassResult { double v[4]; uint32_t nr, mode, used; };
 __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ sconst, const uint32_t tcode_addr,
                                                  const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                  double *__restrict__ list, uint32_t *__restrict__ cnt,
-                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev, const bool ran_fast,
+                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev, const uint32_t round_points,
                                                  const double v0, const double v1, const double v2, const double v3)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const bool ran_fast = round_points == 0;
     CplxPassResult res;
     res.v[0] = v0; res.v[1] = v1; res.v[2] = v2; res.v[3] = v3;
     res.nr = 0;
-    // CTA-wide compaction of the reported points
     const uint32_t mine = __popc(ev);
-    uint32_t incl = mine;
+    uint32_t total, pos;
+    if (ran_fast) {
+        // CTA-wide compaction of the reported points
+        uint32_t incl = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) cnt[warp] = incl;
-    __syncthreads();
-    uint32_t cw = lane < nwarps ? cnt[lane] : 0u, ci = cw;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) cnt[warp] = incl;
+        __syncthreads();
+        uint32_t cw = lane < nwarps ? cnt[lane] : 0u, ci = cw;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, ci, d);
-        if (lane >= d) ci += t;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, ci, d);
+            if (lane >= d) ci += t;
+        }
+        total = __shfl_sync(FULL, ci, 31);
+        pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
+    } else {
+        // a round without a fast pass: every point of the round is on the list (round_points of them: the points of a run
+        // are a prefix of its chunks), each at its own offset -- nothing to count
+        total = round_points;
+        pos = (uint32_t)warp * CHUNK_POINTS + (uint32_t)lane * POINTS_PER_LANE;
     }
-    const uint32_t total = __shfl_sync(FULL, ci, 31);
-    uint32_t pos = __shfl_sync(FULL, ci - cw, warp) + incl - mine;
 #pragma unroll
     for (int j = 0; j < 4; j++)
         if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
@@ -404,20 +413,22 @@ __device__ __noinline__ RoundSlowResult round_slow(const double *__restrict__ sc
                                                    const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                    double *__restrict__ list, uint32_t *__restrict__ cnt,
                                                    const double *__restrict__ xs, const double *__restrict__ ys,
-                                                   const int64_t base, const uint32_t valid, const uint32_t ev_in, const bool ran_fast,
+                                                   const int64_t base, const uint32_t valid, const uint32_t ev_in, const uint32_t round_points,
                                                    const uint32_t quirk_off_plus1, const uint32_t sum_addr,
                                                    const double v0, const double v1, const double v2, const double v3)
 {
     RoundSlowResult out;
     uint32_t ev = ev_in;
     double v[4] = { v0, v1, v2, v3 };
+    uint32_t rp = round_points;
     if (quirk_off_plus1) {
         // eval.clj:109: constant AST whose argument count equals the point count is decoded per argument
         ev = 0;
+        rp = 0;                                       // nothing goes to the complete algebra: an empty compaction
 #pragma unroll
         for (int j = 0; j < 4; j++) v[j] = ((valid >> j) & 1u) ? sconst[quirk_off_plus1 - 1 + base + j] : 0.0;
     }
-    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, deep, list, cnt, xs, base, ev, ran_fast, v[0], v[1], v[2], v[3]);
+    const CplxPassResult cp = cplx_pass(sconst, tcode_addr, slot_addr, leaf_tab, deep, list, cnt, xs, base, ev, rp, v[0], v[1], v[2], v[3]);
     out.nr = cp.nr;
     out.mode = cp.mode;
     out.used = cp.used;                          // the complete algebra was NEEDED: some evaluation left the real line
@@ -583,8 +594,15 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
             continue;
         }
         if (r0 == 0) TR(5);
+        // without a fast pass every point of the round goes to the complete algebra: their number (0 = there was a fast pass)
+        uint32_t round_points = 0;
+        if (!fast) {
+            const int64_t rb = (c_lo + r0) * CHUNK_POINTS, rc = (int64_t)(cnt - r0 < nwarps ? cnt - r0 : nwarps) * CHUNK_POINTS;
+            const int64_t nl = p.n - rb;
+            round_points = (uint32_t)(nl < rc ? (nl > 0 ? nl : 0) : rc);
+        }
         const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
-                                              base, valid, rr.ev, fast, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
+                                              base, valid, rr.ev, round_points, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
         warp_mx = max_nonneg(warp_mx, rs.mx);
         nonreal += __popc(rs.nr);
         used_full |= rs.used;
