@@ -887,8 +887,14 @@ int score_warps(int32_t chunks_per_tile)
         const int v = e ? atoi(e) : 0;
         return (v >= 1 && v <= MAX_SCORE_WARPS && (v & (v - 1)) == 0) ? v : MAX_SCORE_WARPS;
     }();
+    // Tiles of up to 8 chunks get TWO warps per chunk: most programs run such a tile without a fast pass (PF_DOMAIN), and a
+    // chunk is two tasks of the complete algebra -- one per warp, one pass instead of two (100K x 512 / 1024 points -23 % /
+    // -26 %; 16 chunks x 2 = one 32-warp CTA per SM instead of two 16-warp ones: +10 %, so not there).
+    // CLOSYR_WARPS_PER_CHUNK=1 switches it off (measurement knob).
+    static const int per_chunk = [] { const char *e = getenv("CLOSYR_WARPS_PER_CHUNK"); const int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+    const int want = chunks_per_tile <= 8 ? chunks_per_tile * per_chunk : chunks_per_tile;
     int w = 1;
-    while (w < cap && w < chunks_per_tile) w <<= 1;
+    while (w < cap && w < want) w <<= 1;
     return w;
 }
 
