@@ -313,10 +313,12 @@ struct CplxPassResult { double v[4]; uint32_t nr, mode, used; };
 __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ sconst, const uint32_t tcode_addr,
                                                  const uint32_t slot_addr, const double *__restrict__ leaf_tab, const bool deep,
                                                  double *__restrict__ list, uint32_t *__restrict__ cnt,
-                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev, const uint32_t round_points,
+                                                 const double *__restrict__ xs, const int64_t base, const uint32_t ev, const uint32_t round_points_first,
                                                  const double v0, const double v1, const double v2, const double v3)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t round_points = round_points_first >> 1;       // 0: the round had a fast pass
+    const bool first_round = (round_points_first & 1u) != 0;     // of this CTA's tile
     const bool ran_fast = round_points == 0;
     CplxPassResult res;
     res.v[0] = v0; res.v[1] = v1; res.v[2] = v2; res.v[3] = v3;
@@ -347,10 +349,18 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
         total = round_points;
         pos = (uint32_t)warp * CHUNK_POINTS + (uint32_t)lane * POINTS_PER_LANE;
     }
+    // the round's first point (rounds without a fast pass: list entry r is point round_base + r, nothing to store or wait for)
+    const int64_t round_base = base - (int64_t)((uint32_t)warp * CHUNK_POINTS + (uint32_t)lane * POINTS_PER_LANE);
+    if (ran_fast) {
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
-    __syncthreads();
+        for (int j = 0; j < 4; j++)
+            if ((ev >> j) & 1u) list[pos++] = __longlong_as_double(base + j);      // the point's index
+        __syncthreads();
+    } else {
+        pos += mine;
+        // the list still holds the previous round's results until every warp has read its own back
+        if (!first_round) __syncthreads();
+    }
 #ifdef CLOSYR_TRACE
     if (threadIdx.x == 0 && blockIdx.x < TRACE_ITEMS && base < 4096) { g_trace[blockIdx.x * TRACE_SLOTS + 11] = total; g_trace[blockIdx.x * TRACE_SLOTS + 13] = clock64(); }
 #endif
@@ -364,7 +374,8 @@ __device__ __noinline__ CplxPassResult cplx_pass(const double *__restrict__ scon
 #pragma unroll
         for (int j = 0; j < CPLX_POINTS; j++) {
             const uint32_t r = t0 + j * 32 + lane;
-            ca.idx[j] = __double_as_longlong(list[r < total ? r : t0]);          // idle lanes repeat the task's first point
+            const uint32_t q = r < total ? r : t0;                               // idle lanes repeat the task's first point
+            ca.idx[j] = ran_fast ? __double_as_longlong(list[q]) : round_base + q;
         }
         const CplxResult<CPLX_POINTS> cr = deep ? run_cplx<CPLX_POINTS, true>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab)
                                                 : run_cplx<CPLX_POINTS, false>(tcode_addr, slot_addr, sconst, xs, ca, leaf_tab);
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(MAX_SCORE_WARPS * 32, 1) score_kernel(const Sc
         if (!fast) {
             const int64_t rb = (c_lo + r0) * CHUNK_POINTS, rc = (int64_t)(cnt - r0 < nwarps ? cnt - r0 : nwarps) * CHUNK_POINTS;
             const int64_t nl = p.n - rb;
-            round_points = (uint32_t)(nl < rc ? (nl > 0 ? nl : 0) : rc);
+            round_points = (uint32_t)(nl < rc ? (nl > 0 ? nl : 0) : rc) << 1 | (r0 == 0 ? 1u : 0u);     // bit 0: the tile's first round
         }
         const RoundSlowResult rs = round_slow(sconst, tcode_addr, slot_addr, p.leaf_tab, (pflags & PF_DEEP) != 0, list, s_counts + parity * 32, p.xs, p.ys,
                                               base, valid, rr.ev, round_points, quirk_off_plus1, sum_addr, rr.v[0], rr.v[1], rr.v[2], rr.v[3]);
