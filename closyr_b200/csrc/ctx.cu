@@ -333,9 +333,10 @@ int launch_range(closyr_ctx *ctx, DeviceState &d, int32_t max_leafs, int64_t c_l
     sp.warps = score_warps(cpt);
     sp.n_tiles = n_tiles;
     {
-        // grouped CTA order: pays when several CTAs share an SM (short tiles); CLOSYR_ORDER=0 / 1 forces it off / on
+        // grouped CTA order: pays most when several CTAs share an SM (short tiles: -20 %), still -1 % with one program per SM
+        // since the programs that skip the fast pass are grouped together; CLOSYR_ORDER=0 switches it off
         static const int force = [] { const char *e = getenv("CLOSYR_ORDER"); return e ? atoi(e) : -1; }();
-        if (force == 1 || (force < 0 && sp.warps < 32)) {
+        if (force != 0) {
             if (!d.pop.ordered) {
                 CU(ctx, d.pop.order.reserve((size_t)ne * 4));
                 launch_order((const uint32_t *)d.pop.key.p, ne, (uint32_t *)d.pop.order.p, d.stream);
