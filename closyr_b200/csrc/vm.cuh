@@ -1036,6 +1036,10 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "@p_ bra.uni X_" S ";\n\t"                   \
     "add.u32 t_, aux" S "_, %8;\n\t"             \
     "ld.shared.f64 s0_, [t_];\n\t ld.shared.f64 s1_, [t_+256];\n\t"
+#define CLOSYR_TRIG2_GUARD(S)                                                               \
+    "mov.b64 {t_, u0_}, %0;\n\t mov.b64 {t_, u1_}, %1;\n\t"                                    \
+    "and.b32 u0_, u0_, 0x7fffffff;\n\t and.b32 u1_, u1_, 0x7fffffff;\n\t max.u32 u0_, u0_, u1_;\n\t" \
+    "setp.ge.u32 p_, u0_, 0x4197d784;\n\t vote.sync.any.pred p_, p_, 0xffffffff;\n\t @p_ bra.uni X_" S ";\n\t"
 #define CLOSYR_CHEAP2_HANDLERS(S, T, OFF)                                                         \
     "LDXP_" S ":\n\t" CLOSYR_PUSH2_PTX(S)                                                      \
     "LDX_" S ":\n\t mov.f64 %0, %9;\n\t mov.f64 %1, %10;\n\t bra.uni NEXT_" T ";\n\t"          \
@@ -1062,12 +1066,44 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "bra.uni NEXT_" T ";\n\t"                                                                  \
     "ADDS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("add.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
     "MULS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("mul.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
+    /* sin / cos of the accumulator in real mode: the operations of v_sin<2> / v_cos<2> (vmath.cuh), bit for bit; an argument  \
+       the lean routine hands to the library (|x| >= 1e8, Inf, NaN: any lane, either point) leaves the block */               \
+    "SIN_" S ":\n\t" CLOSYR_TRIG2_GUARD(S)                                                     \
+    "ld.const.f64 c_, [closyr_vm_c+112];\n\t ld.const.f64 s0_, [closyr_vm_c+8];\n\t"           \
+    "fma.rn.f64 ta_, %0, c_, s0_;\n\t fma.rn.f64 tb_, %1, c_, s0_;\n\t"                        \
+    "sub.rn.f64 ka_, ta_, s0_;\n\t sub.rn.f64 kb_, tb_, s0_;\n\t"                              \
+    "bra.uni TRIG_" S ";\n\t"                                                                  \
+    "COS_" S ":\n\t" CLOSYR_TRIG2_GUARD(S)                                                     \
+    "ld.const.f64 c_, [closyr_vm_c+112];\n\t ld.const.f64 s0_, [closyr_vm_c+8];\n\t ld.const.f64 s1_, [closyr_vm_c+256];\n\t" \
+    "fma.rn.f64 ta_, %0, c_, s1_;\n\t fma.rn.f64 tb_, %1, c_, s1_;\n\t"                        \
+    "add.rn.f64 ta_, ta_, s0_;\n\t add.rn.f64 tb_, tb_, s0_;\n\t"                              \
+    "sub.rn.f64 ka_, ta_, s0_;\n\t sub.rn.f64 kb_, tb_, s0_;\n\t"                              \
+    "sub.rn.f64 ka_, ka_, s1_;\n\t sub.rn.f64 kb_, kb_, s1_;\n\t"                              \
+    "TRIG_" S ":\n\t" /* r = x - k pi (three terms), sin(r) = r + r z Q(z), sign by the parity of k (low word of t) */ \
+    "neg.f64 ka_, ka_;\n\t neg.f64 kb_, kb_;\n\t"                                              \
+    "ld.const.f64 c_, [closyr_vm_c+120];\n\t fma.rn.f64 ra_, ka_, c_, %0;\n\t fma.rn.f64 rb_, kb_, c_, %1;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+128];\n\t fma.rn.f64 ra_, ka_, c_, ra_;\n\t fma.rn.f64 rb_, kb_, c_, rb_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+184];\n\t fma.rn.f64 ra_, ka_, c_, ra_;\n\t fma.rn.f64 rb_, kb_, c_, rb_;\n\t" \
+    "mul.rn.f64 za_, ra_, ra_;\n\t mul.rn.f64 zb_, rb_, rb_;\n\t"                              \
+    "ld.const.f64 ka_, [closyr_vm_c+248];\n\t mov.f64 kb_, ka_;\n\t"                           \
+    "ld.const.f64 c_, [closyr_vm_c+240];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+232];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+224];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+216];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+208];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+200];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+192];\n\t fma.rn.f64 ka_, ka_, za_, c_;\n\t fma.rn.f64 kb_, kb_, zb_, c_;\n\t" \
+    "mul.rn.f64 ka_, ka_, za_;\n\t mul.rn.f64 kb_, kb_, zb_;\n\t"                              \
+    "fma.rn.f64 ra_, ka_, ra_, ra_;\n\t fma.rn.f64 rb_, kb_, rb_, rb_;\n\t"                    \
+    "mov.b64 {t_, u0_}, ta_;\n\t shl.b32 t_, t_, 31;\n\t mov.b64 {u1_, u0_}, ra_;\n\t xor.b32 u0_, u0_, t_;\n\t mov.b64 %0, {u1_, u0_};\n\t" \
+    "mov.b64 {t_, u0_}, tb_;\n\t shl.b32 t_, t_, 31;\n\t mov.b64 {u1_, u0_}, rb_;\n\t xor.b32 u0_, u0_, t_;\n\t mov.b64 %1, {u1_, u0_};\n\t" \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
     "NEXT_" S ":\n\t"                                                                          \
     "ld.shared.v4.b32 {h" T "_, aux" T "_, lo" T "_, hi" T "_}, [%2" OFF "];\n\t"                \
     "add.u32 %2, %2, 16;\n\t"                                                                  \
     "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", X_" S ", X_" S \
     ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S      \
-    ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S   \
+    ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", SIN_" S ", COS_" S ", X_" S ", X_" S \
     ", X_" S ", X_" S ", X_" S ", X_" S ";\n\t"                                                \
     "brx.idx.uni h" S "_, tbl" S "_;\n\t"                                                      \
     "X_" S ":\n\t"                                                                             \
@@ -1160,7 +1196,8 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
                 ".reg .pred p_;\n\t"
                 ".reg .b32 t_, z_, hA_, auxA_, loA_, hiA_, hB_, auxB_, loB_, hiB_;\n\t"
                 ".reg .b64 ad_, a0_, a1_;\n\t"
-                ".reg .f64 c_, s0_, s1_;\n\t"
+                ".reg .f64 c_, s0_, s1_, ta_, tb_, ka_, kb_, ra_, rb_, za_, zb_;\n\t"
+                ".reg .b32 u0_, u1_;\n\t"
                 "mov.b32 z_, 0;\n\t"
                 "bra.uni NEXT_A;\n\t"
                 CLOSYR_CHEAP2_HANDLERS("A", "A", "")
@@ -1360,6 +1397,7 @@ __device__ __noinline__ CplxResult<P> run_cplx(const uint32_t tcode_addr, const 
 #undef CLOSYR_TO_COMPLEX
 }
 #undef CLOSYR_CHEAP2_HANDLERS
+#undef CLOSYR_TRIG2_GUARD
 #undef CLOSYR_SLOT_REAL_OR_EXIT
 #undef CLOSYR_OP2
 #undef CLOSYR_PUSH2_PTX
