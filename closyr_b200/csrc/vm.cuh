@@ -1068,6 +1068,38 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "MULS_" S ":\n\t" CLOSYR_SLOT_REAL_OR_EXIT(S) CLOSYR_OP2("mul.rn.f64", "s0_", "s1_") "bra.uni NEXT_" T ";\n\t" \
     /* sin / cos of the accumulator in real mode: the operations of v_sin<2> / v_cos<2> (vmath.cuh), bit for bit; an argument  \
        the lean routine hands to the library (|x| >= 1e8, Inf, NaN: any lane, either point) leaves the block */               \
+    /* 1 / acc in real mode (zero is a pole: ComplexInfinity, the C++ handler's business) */       \
+    "RECIP_" S ":\n\t"                                                                         \
+    "setp.eq.f64 p_, %0, 0d0000000000000000;\n\t setp.eq.or.f64 p_, %1, 0d0000000000000000, p_;\n\t" \
+    "vote.sync.any.pred p_, p_, 0xffffffff;\n\t @p_ bra.uni X_" S ";\n\t"                      \
+    "ld.const.f64 c_, [closyr_vm_c+280];\n\t div.rn.f64 %0, c_, %0;\n\t div.rn.f64 %1, c_, %1;\n\t" \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
+    /* exp of the accumulator: v_exp<2> bit for bit; |x| >= 700, Inf, NaN leave the block */    \
+    "EXP_" S ":\n\t"                                                                           \
+    "mov.b64 {t_, u0_}, %0;\n\t mov.b64 {t_, u1_}, %1;\n\t"                                    \
+    "and.b32 u0_, u0_, 0x7fffffff;\n\t and.b32 u1_, u1_, 0x7fffffff;\n\t max.u32 u0_, u0_, u1_;\n\t" \
+    "setp.ge.u32 p_, u0_, 0x4085e000;\n\t vote.sync.any.pred p_, p_, 0xffffffff;\n\t @p_ bra.uni X_" S ";\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+0];\n\t ld.const.f64 s0_, [closyr_vm_c+8];\n\t"             \
+    "fma.rn.f64 ta_, %0, c_, s0_;\n\t fma.rn.f64 tb_, %1, c_, s0_;\n\t"                        \
+    "sub.rn.f64 ka_, ta_, s0_;\n\t sub.rn.f64 kb_, tb_, s0_;\n\t"                              \
+    "neg.f64 ka_, ka_;\n\t neg.f64 kb_, kb_;\n\t"                                              \
+    "ld.const.f64 c_, [closyr_vm_c+16];\n\t fma.rn.f64 ra_, ka_, c_, %0;\n\t fma.rn.f64 rb_, kb_, c_, %1;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+24];\n\t fma.rn.f64 ra_, ka_, c_, ra_;\n\t fma.rn.f64 rb_, kb_, c_, rb_;\n\t" \
+    "ld.const.f64 ka_, [closyr_vm_c+32];\n\t mov.f64 kb_, ka_;\n\t"                            \
+    "ld.const.f64 c_, [closyr_vm_c+40];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+48];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+56];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+64];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+72];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+80];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+88];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+96];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+104];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "ld.const.f64 c_, [closyr_vm_c+280];\n\t fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t" \
+    "fma.rn.f64 ka_, ka_, ra_, c_;\n\t fma.rn.f64 kb_, kb_, rb_, c_;\n\t"                      \
+    "mov.b64 {t_, u0_}, ta_;\n\t shl.b32 t_, t_, 20;\n\t mov.b64 {u1_, u0_}, ka_;\n\t add.s32 u0_, u0_, t_;\n\t mov.b64 %0, {u1_, u0_};\n\t" \
+    "mov.b64 {t_, u0_}, tb_;\n\t shl.b32 t_, t_, 20;\n\t mov.b64 {u1_, u0_}, kb_;\n\t add.s32 u0_, u0_, t_;\n\t mov.b64 %1, {u1_, u0_};\n\t" \
+    "bra.uni NEXT_" T ";\n\t"                                                                  \
     "SIN_" S ":\n\t" CLOSYR_TRIG2_GUARD(S)                                                     \
     "ld.const.f64 c_, [closyr_vm_c+112];\n\t ld.const.f64 s0_, [closyr_vm_c+8];\n\t"           \
     "fma.rn.f64 ta_, %0, c_, s0_;\n\t fma.rn.f64 tb_, %1, c_, s0_;\n\t"                        \
@@ -1103,7 +1135,7 @@ template <int P> struct CplxResult { double out[P]; uint32_t nonreal, left_real;
     "add.u32 %2, %2, 16;\n\t"                                                                  \
     "tbl" S "_: .branchtargets X_" S ", LDX_" S ", LDXP_" S ", LDC_" S ", LDCP_" S ", TAB_" S ", TABP_" S ", X_" S ", X_" S \
     ", ADDX_" S ", ADDC_" S ", MULX_" S ", MULC_" S ", NEG_" S ", SQR_" S ", ABS_" S ", ST_" S ", ADDS_" S ", MULS_" S      \
-    ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", X_" S ", SIN_" S ", COS_" S ", X_" S ", X_" S \
+    ", X_" S ", X_" S ", RECIP_" S ", X_" S ", X_" S ", X_" S ", X_" S ", EXP_" S ", X_" S ", SIN_" S ", COS_" S ", X_" S ", X_" S \
     ", X_" S ", X_" S ", X_" S ", X_" S ";\n\t"                                                \
     "brx.idx.uni h" S "_, tbl" S "_;\n\t"                                                      \
     "X_" S ":\n\t"                                                                             \
